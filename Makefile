@@ -1,0 +1,37 @@
+# Builds libb2resample.so (CUDA, sm_100a only) and the b2resample CLI in-tree.
+# Usage: make -j8            (nvcc cross-compiles without a GPU)
+NVCC      ?= nvcc
+CXX       ?= g++
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := -std=c++17 -O3 -lineinfo $(ARCH) --expt-relaxed-constexpr -Xcompiler -fPIC $(NVCC_EXTRA)
+SRC       := vkresample_b200/csrc
+OUT       := vkresample_b200/lib
+OBJ       := build/obj
+CU_SRCS   := b2r_api.cu b2r_static_r2c.cu b2r_static_c2r.cu b2r_static_cols.cu b2r_dynamic.cu b2r_sharpen.cu
+OBJS      := $(addprefix $(OBJ)/,$(CU_SRCS:.cu=.o)) $(OBJ)/b2r_plan.o
+HDRS      := $(wildcard $(SRC)/*.cuh $(SRC)/*.h) include/b2resample.h
+
+all: $(OUT)/libb2resample.so $(OUT)/b2resample
+
+$(OBJ)/%.o: $(SRC)/%.cu $(HDRS)
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -Xptxas -v -c $< -o $@ 2> $(OBJ)/$*.ptxas.log || (cat $(OBJ)/$*.ptxas.log; exit 1)
+
+$(OBJ)/b2r_plan.o: $(SRC)/b2r_plan.cpp $(HDRS)
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -x cu -c $< -o $@
+
+$(OUT)/libb2resample.so: $(OBJS)
+	@mkdir -p $(OUT)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS)
+
+$(OUT)/b2resample: $(SRC)/cli.cpp $(OUT)/libb2resample.so include/b2resample.h
+	$(CXX) -std=c++17 -O2 -Iinclude $< -o $@ -L$(OUT) -lb2resample -lz -lpthread -Wl,-rpath,'$$ORIGIN'
+
+emu:
+	tests/emu/build.sh
+
+clean:
+	rm -rf build $(OUT)/libb2resample.so $(OUT)/b2resample
+
+.PHONY: all emu clean

@@ -1,0 +1,261 @@
+// tests/emu/emu.cpp -- CPU thread emulator for the CUDA kernels.  TEST INFRASTRUCTURE ONLY.
+//
+// The authoring container has no GPU.  To check the index arithmetic of every kernel before
+// spending GPU time, this file compiles the *same* kernel source (b2r_kernels.cuh) as plain C++
+// (-DB2R_HOST_EMU): each CUDA thread of a CTA becomes an OS thread, __syncthreads() a
+// std::barrier, dynamic shared memory a heap block.  CTAs run one after another.  It is built
+// into tests/emu/libb2r_emu.so by tests/emu/build.sh and driven by tests/test_emu_kernels.py.
+// The product library (libb2resample.so) never links or calls any of this.
+#include <barrier>
+#include <cstdio>
+#include <cstring>
+#include <functional>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../vkresample_b200/csrc/b2r_kernels.cuh"
+#include "../../vkresample_b200/csrc/b2r_plan.h"
+#include "../../vkresample_b200/csrc/b2r_static_sizes.h"
+
+namespace b2r_emu {
+thread_local Ctx g_ctx;
+
+struct Dim3 { unsigned x = 1, y = 1, z = 1; };
+
+static void launch(Dim3 grid, Dim3 block, size_t smem_bytes, const std::function<void()>& body) {
+    const unsigned nthreads = block.x * block.y;
+    std::barrier bar((std::ptrdiff_t)nthreads);
+    std::vector<unsigned char> smem(smem_bytes + 64, 0);
+    auto sync_fn = [](void* p) { static_cast<std::barrier<>*>(p)->arrive_and_wait(); };
+    auto worker = [&](unsigned t) {
+        for (unsigned bz = 0; bz < grid.z; ++bz)
+            for (unsigned by = 0; by < grid.y; ++by)
+                for (unsigned bx = 0; bx < grid.x; ++bx) {
+                    Ctx& c = g_ctx;
+                    c.tid_x = t % block.x; c.tid_y = t / block.x;
+                    c.bid_x = bx; c.bid_y = by; c.bid_z = bz;
+                    c.bdim_x = block.x; c.bdim_y = block.y;
+                    c.gdim_x = grid.x; c.gdim_y = grid.y; c.gdim_z = grid.z;
+                    c.smem = smem.data();
+                    c.sync = sync_fn; c.sync_arg = &bar;
+                    body();
+                    bar.arrive_and_wait();  // CTA boundary: shared memory is reused
+                }
+    };
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nthreads; ++t) th.emplace_back(worker, t);
+    for (auto& x : th) x.join();
+}
+}  // namespace b2r_emu
+
+using namespace b2r;
+
+// generic single-sequence complex FFT through the stage engine (tests every radix / size)
+template <int DIR, class P>
+static void k_fft_test(const float2* in, float2* out, const float2* tw, const P plan) {
+    const int T = (int)B2R_BDIM_X, tid = (int)B2R_TID_X;
+    float2* sm = B2R_SMEM(float2);
+    for (int i = tid; i < plan.n(); i += T) sm[smem_pad(i)] = in[i];
+    B2R_SYNC();
+    plan.template for_stages<0, 0>([&](auto st, int) {
+        using St = decltype(st);
+        float2 v[St::NB][St::R];
+        stage_load_compute<DIR>(st, sm, tw, T, tid, 1, 0, v);
+        B2R_SYNC();
+        stage_store(st, sm, T, tid, 1, 0, v);
+        B2R_SYNC();
+    });
+    for (int i = tid; i < plan.n(); i += T) out[i] = sm[smem_pad(i)];
+}
+
+static FrameDims dims_of(const Geometry& g) {
+    FrameDims d{};
+    d.w = g.w; d.h = g.h; d.up_w = g.up_w; d.up_h = g.up_h; d.nx = g.nx; d.spec_stride = g.spec_stride;
+    d.zp_lo = g.zp_lo; d.zp_hi = g.zp_hi; d.neg_shift = g.neg_shift;
+    d.in_plane = g.in_plane; d.pre_plane = g.pre_plane; d.out_plane = g.out_plane;
+    d.up2 = g.up2; d.sharpen = g.sharpen;
+    return d;
+}
+
+template <class P> static void host_fft_of(HostFft* hf) {
+    int r[kMaxStages];
+    for (int s = 0; s < P::kStages; ++s) r[s] = P::radix(s);
+    build_fft(P::kN, r, P::kStages, P::kT, hf);
+}
+
+using b2r_emu::Dim3;
+
+struct FrameCtx {
+    Geometry g; FrameDims dm; int precision;
+    const void* in; void* out;
+    std::vector<float2> spec1, spec2;
+    std::vector<unsigned char> pre;
+};
+
+template <class P, int PPB> static void emu_r2c(FrameCtx& c, const P plan, const HostFft& hf) {
+    int pairs = 3 * c.g.h / 2;
+    Dim3 grid, block; block.x = hf.desc.threads; block.y = PPB; grid.x = (pairs + PPB - 1) / PPB;
+    const float2* tw = hf.twiddles.data();
+    b2r_emu::launch(grid, block, PPB * smem_padded_len(c.g.w) * sizeof(float2), [&] {
+        if (c.precision == 2) k_r2c_rows<P, __half, PPB>((const __half*)c.in, c.spec1.data(), tw, plan, c.dm, pairs);
+        else k_r2c_rows<P, float, PPB>((const float*)c.in, c.spec1.data(), tw, plan, c.dm, pairs);
+    });
+}
+template <class P, int PPB> static void emu_c2r(FrameCtx& c, const P plan, const HostFft& hf) {
+    int pairs = 3 * c.g.up_h / 2;
+    Dim3 grid, block; block.x = hf.desc.threads; block.y = PPB; grid.x = (pairs + PPB - 1) / PPB;
+    const float2* tw = hf.twiddles.data();
+    const float scale = 1.0f / (float)c.g.up_w;
+    b2r_emu::launch(grid, block, PPB * smem_padded_len(c.g.up_w) * sizeof(float2), [&] {
+        if (c.precision == 2) k_c2r_rows<P, __half, PPB>(c.spec2.data(), (__half*)c.pre.data(), tw, plan, c.dm, pairs, scale);
+        else k_c2r_rows<P, float, PPB>(c.spec2.data(), (float*)c.pre.data(), tw, plan, c.dm, pairs, scale);
+    });
+}
+template <class PF, class PI, int CC>
+static void emu_cols(FrameCtx& c, const PF pf, const PI pi, const HostFft& hf, const HostFft& hi) {
+    Dim3 grid, block; block.x = CC * hi.desc.threads; grid.x = (c.g.nx + CC - 1) / CC; grid.y = 3;
+    const float2 *twf = hf.twiddles.data(), *twi = hi.twiddles.data();
+    const float scale = 1.0f / (float)c.g.up_h;
+    b2r_emu::launch(grid, block, smem_padded_len(c.g.up_h * CC) * sizeof(float2), [&] {
+        k_cols<PF, PI, CC>(c.spec1.data(), c.spec2.data(), twf, twi, pf, pi, c.dm, scale);
+    });
+}
+
+extern "C" {
+
+// returns number of stages (>0) or -1; radices[] receives the schedule
+int b2r_emu_schedule(int n, int* radices, int* threads) {
+    HostFft hf; std::string err;
+    if (!schedule_fft(n, &hf, &err)) return -1;
+    for (int s = 0; s < hf.desc.nstages; ++s) radices[s] = hf.desc.st[s].radix;
+    *threads = hf.desc.threads;
+    return hf.desc.nstages;
+}
+
+// use_static != 0: run the ahead-of-time schedule for n if one exists (returns 1 if it did)
+int b2r_emu_fft(int n, int dir, int use_static, const float* in, float* out) {
+    HostFft hf; std::string err;
+    Dim3 grid, block;
+    if (use_static) {
+#define X(N, PPB, T, ...)                                                                          \
+        if (n == N) {                                                                              \
+            using P = StaticFft<N, T, __VA_ARGS__>;                                                \
+            host_fft_of<P>(&hf); block.x = T;                                                      \
+            const float2* tw = hf.twiddles.data();                                                 \
+            b2r_emu::launch(grid, block, smem_padded_len(n) * sizeof(float2), [&] {                \
+                if (dir < 0) k_fft_test<-1>((const float2*)in, (float2*)out, tw, P{});             \
+                else k_fft_test<+1>((const float2*)in, (float2*)out, tw, P{});                     \
+            });                                                                                    \
+            return 1;                                                                              \
+        }
+        B2R_STATIC_ROWS(X)
+#undef X
+    }
+    if (!schedule_fft(n, &hf, &err)) return -1;
+    block.x = (unsigned)hf.desc.threads;
+    const float2* tw = hf.twiddles.data();
+    const DynFft plan{&hf.desc};
+    b2r_emu::launch(grid, block, smem_padded_len(n) * sizeof(float2), [&] {
+        if (dir < 0) k_fft_test<-1>((const float2*)in, (float2*)out, tw, plan);
+        else k_fft_test<+1>((const float2*)in, (float2*)out, tw, plan);
+    });
+    return 0;
+}
+
+// Runs the 4-kernel frame on the CPU emulator.  Buffers as in the C-ABI (input: reference layout
+// with (W+2)*H plane stride; output compact).  Optional dumps: spec1 [3][H][stride] complex,
+// spec2 [3][upH][stride] complex, pre [3*(upW+2)*upH + slack] elements.
+// use_static: prefer the ahead-of-time schedules (as the product does); cc only affects the
+// dynamic column kernel.  *used_static gets bit0 K1, bit1 columns, bit2 K7.
+int b2r_emu_frame(int w, int h, float upscale, int precision, float sharpen_const, float up2_lit, int cc,
+                  int use_static, const void* in, void* out, float* spec1_dump, float* spec2_dump,
+                  void* pre_dump, int* spec_stride_out, int* used_static) {
+    FrameCtx c; std::string err;
+    Geometry& g = c.g;
+    if (!make_geometry(w, h, upscale, precision, sharpen_const, &g, &err)) { fprintf(stderr, "%s\n", err.c_str()); return -1; }
+    g.up2 = up2_lit;
+    c.dm = dims_of(g); c.precision = precision; c.in = in; c.out = out;
+    if (spec_stride_out) *spec_stride_out = g.spec_stride;
+    c.spec1.assign(g.spec_in_elems(), make_float2(0, 0));
+    c.spec2.assign(g.spec_out_elems(), make_float2(0, 0));
+    c.pre.assign(g.pre_elems * g.elem_bytes(), 0);
+    int used = 0;
+    HostFft hf, hi;
+    {   // K1
+        bool done = false;
+        if (use_static) {
+#define X(N, PPB, T, ...) \
+            if (!done && g.w == N) { using P = StaticFft<N, T, __VA_ARGS__>; host_fft_of<P>(&hf); emu_r2c<P, PPB>(c, P{}, hf); done = true; used |= 1; }
+            B2R_STATIC_ROWS(X)
+#undef X
+        }
+        if (!done) {
+            if (!schedule_fft(g.w, &hf, &err)) return -2;
+            emu_r2c<DynFft, 1>(c, DynFft{&hf.desc}, hf);
+        }
+    }
+    {   // K2..K6
+        bool done = false;
+        if (use_static) {
+#define X(H, UPH, CC, PF, PI) \
+            if (!done && g.h == H && g.up_h == UPH) { host_fft_of<PF>(&hf); host_fft_of<PI>(&hi); emu_cols<PF, PI, CC>(c, PF{}, PI{}, hf, hi); done = true; used |= 2; }
+            B2R_STATIC_COLS(X)
+#undef X
+        }
+        if (!done) {
+            if (!schedule_fft(g.h, &hf, &err) || !schedule_fft(g.up_h, &hi, &err)) return -2;
+            int tc = std::max(hf.desc.threads, hi.desc.threads);
+            schedule_fft(g.h, &hf, &err, tc); schedule_fft(g.up_h, &hi, &err, tc);
+            const DynFft pf{&hf.desc}, pi{&hi.desc};
+            if (cc == 8) emu_cols<DynFft, DynFft, 8>(c, pf, pi, hf, hi);
+            else if (cc == 4) emu_cols<DynFft, DynFft, 4>(c, pf, pi, hf, hi);
+            else emu_cols<DynFft, DynFft, 2>(c, pf, pi, hf, hi);
+        }
+    }
+    {   // K7
+        bool done = false;
+        if (use_static) {
+#define X(N, PPB, T, ...) \
+            if (!done && g.up_w == N) { using P = StaticFft<N, T, __VA_ARGS__>; host_fft_of<P>(&hf); emu_c2r<P, PPB>(c, P{}, hf); done = true; used |= 4; }
+            B2R_STATIC_ROWS(X)
+#undef X
+        }
+        if (!done) {
+            if (!schedule_fft(g.up_w, &hf, &err)) return -2;
+            emu_c2r<DynFft, 1>(c, DynFft{&hf.desc}, hf);
+        }
+    }
+    {   // K8
+        constexpr int PX = 4;
+        Dim3 grid, block; block.x = 64; grid.x = (g.up_w + PX * 64 - 1) / (PX * 64); grid.y = g.up_h; grid.z = 3;
+        const FrameDims dm = c.dm;
+        b2r_emu::launch(grid, block, 0, [&] {
+            if (precision == 2) k_sharpen<__half, PX>((const __half*)c.pre.data(), (__half*)out, dm);
+            else k_sharpen<float, PX>((const float*)c.pre.data(), (float*)out, dm);
+        });
+    }
+    if (used_static) *used_static = used;
+    if (spec1_dump) memcpy(spec1_dump, c.spec1.data(), c.spec1.size() * sizeof(float2));
+    if (spec2_dump) memcpy(spec2_dump, c.spec2.data(), c.spec2.size() * sizeof(float2));
+    if (pre_dump) memcpy(pre_dump, c.pre.data(), c.pre.size());
+    return 0;
+}
+
+// sharpen alone on a caller-provided padded plane buffer (bit-exactness test of K8)
+int b2r_emu_sharpen(int w, int h, float upscale, int precision, float sharpen_const, float up2_lit,
+                    const void* pre, void* out) {
+    Geometry g; std::string err;
+    if (!make_geometry(w, h, upscale, precision, sharpen_const, &g, &err)) return -1;
+    g.up2 = up2_lit;
+    const FrameDims dm = dims_of(g);
+    constexpr int PX = 4;
+    b2r_emu::Dim3 grid, block; block.x = 64; grid.x = (g.up_w + PX * 64 - 1) / (PX * 64); grid.y = g.up_h; grid.z = 3;
+    b2r_emu::launch(grid, block, 0, [&] {
+        if (precision == 2) k_sharpen<__half, PX>((const __half*)pre, (__half*)out, dm);
+        else k_sharpen<float, PX>((const float*)pre, (float*)out, dm);
+    });
+    return 0;
+}
+
+}  // extern "C"

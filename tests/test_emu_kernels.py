@@ -1,0 +1,132 @@
+"""CPU-emulated runs of the CUDA kernel source against the oracle (no GPU needed).
+
+The kernels in vkresample_b200/csrc/b2r_kernels.cuh are compiled as plain C++ by tests/emu (one OS
+thread per CUDA thread) so that their index arithmetic -- Stockham stages for every radix, the R2C
+split, the fused shift/zero-pad remap, the C2R pack with the reference's complex-DC quirk, the
+sharpen's flat neighbour rule -- is checked here; the -m gpu tests repeat the comparison through
+the real library on the B200."""
+import numpy as np
+import pytest
+import scipy.fft as sf
+
+import emu_util as eu
+from oracle import vkresample_oracle as vo
+
+SIZES = [2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 14, 15, 16, 18, 20, 21, 24, 25, 27, 28, 30, 32, 35, 36, 42, 45, 48, 49,
+         50, 54, 56, 60, 63, 64, 70, 72, 75, 80, 81, 84, 90, 96, 98, 100, 105, 108, 112, 120, 125, 126, 128, 135,
+         144, 147, 150, 160, 162, 168, 175, 180, 192, 196, 200, 210, 216, 224, 225, 240, 243, 245, 250, 252, 256,
+         270, 288, 300, 320, 343, 360, 375, 384, 400, 405, 420, 432, 448, 450, 480, 486, 490, 500, 504, 512, 540,
+         576, 600, 625, 630, 640, 672, 686, 700, 720, 729, 750, 768, 784, 800, 810, 840, 864, 875, 896, 900, 945,
+         960, 972, 980, 1000, 1024, 1080]
+
+
+def test_dynamic_stage_engine_all_radices():
+    """every radix 2..16 (incl. composite 6, 9, 10, 12, 14, 15) through the runtime dispatcher"""
+    rng = np.random.default_rng(0)
+    seen = set()
+    for n in SIZES:
+        rad, _ = eu.schedule(n)
+        assert rad is not None and int(np.prod(rad)) == n
+        seen.update(rad)
+        x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+        for d in (-1, 1):
+            out, _ = eu.fft(x, d)
+            ref = np.fft.fft(x.astype(np.complex128)) if d < 0 else np.fft.ifft(x.astype(np.complex128)) * n
+            assert np.abs(out - ref).max() <= 2e-6 * np.abs(ref).max(), (n, d, rad)
+    assert seen == {2, 3, 4, 5, 6, 7, 8, 9, 10, 12, 14, 15, 16}
+
+
+def test_unschedulable_sizes_rejected():
+    for n in (11, 13, 22, 26, 1 << 16):
+        assert eu.schedule(n)[0] is None
+
+
+@pytest.mark.parametrize("n", [256, 512, 1024, 2048, 4096, 1920, 3840, 7680])
+def test_static_schedules(n):
+    """the ahead-of-time schedules of the BASELINE sizes (b2r_static_sizes.h)"""
+    rng = np.random.default_rng(n)
+    x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    for d in (-1, 1):
+        out, was_static = eu.fft(x, d, use_static=True)
+        assert was_static == 1
+        ref = np.fft.fft(x.astype(np.complex128)) if d < 0 else np.fft.ifft(x.astype(np.complex128)) * n
+        assert np.abs(out - ref).max() <= 2e-6 * np.abs(ref).max()
+
+
+def _check_frame(w, h, up, prec, s, kind, cc=4, use_static=True, expect_static=None):
+    plan = vo.make_plan(w, h, up)
+    x = vo.synthetic_frame(kind, w, h)
+    dt = np.float16 if prec == 2 else np.float32
+    xin = x.astype(dt)
+    r = eu.frame(xin, up, prec, s, plan, cc=cc, use_static=use_static)
+    if expect_static is not None:
+        assert r["used_static"] == expect_static
+    # stage 1: row spectra (rfft along x)
+    f_rows = sf.rfft(xin.astype(np.float64), axis=-1)
+    assert np.abs(r["spec1"] - f_rows).max() <= 2e-6 * np.abs(f_rows).max()
+    # stage 2: column FFT + shift/zero-pad + inverse column FFT
+    f2 = vo.forward_spectrum(xin.astype(np.float64))
+    b = vo.shift_zero_pad(f2, plan)
+    g = sf.ifft(b, axis=-2)[:, :, :w // 2 + 1]
+    assert np.abs(r["spec2"] - g).max() <= 2e-6 * np.abs(g).max()
+    # stage 3: C2R incl. the complex-DC quirk; tolerance 1e-5 on the x up^2 plane (fp32)
+    pre_o = vo.store_pre_sharpen(vo.inverse_plane(b, plan), prec)
+    e_pre = np.abs(r["pre"].astype(np.float64) - pre_o.astype(np.float64)).max() * plan.up2
+    assert e_pre <= (1e-5 if prec == 0 else 2e-3), e_pre
+    # stage 4: sharpen is bit-exact given identical input
+    sh = vo.sharpen(r["pre"], plan, s, prec)
+    assert np.array_equal(sh.view(np.uint16 if prec == 2 else np.uint32),
+                          r["out"].view(np.uint16 if prec == 2 else np.uint32))
+    # end to end against the float64 oracle
+    o64 = vo.upscale_frame(xin, up, s, prec, dtype=np.float64)
+    e = np.abs(r["out"].astype(np.float64) - o64).max()
+    assert e <= (1e-4 if prec == 0 else 1e-2), e
+    return e
+
+
+def test_frame_c1_static_fp32():
+    """BASELINE config 1 (256x128 -> 512x256 fp32) through the ahead-of-time schedules"""
+    _check_frame(256, 128, 2.0, 0, 0.2, "noise", expect_static=7)
+
+
+def test_frame_c1_static_fp16():
+    _check_frame(256, 128, 2.0, 2, 0.2, "smooth", expect_static=7)
+
+
+@pytest.mark.parametrize("w,h,up,prec,cc", [
+    (32, 16, 2.0, 0, 4), (64, 32, 2.0, 0, 8), (60, 36, 2.0, 0, 4), (48, 20, 1.5, 0, 2),
+    (64, 32, 2.0, 2, 4), (56, 28, 3.0, 0, 4), (40, 24, 1.0, 0, 4), (36, 20, 2.5, 2, 2)])
+def test_frame_dynamic(w, h, up, prec, cc):
+    """any-size path: non power-of-two sizes (radix 3/5/7), non-integer and odd factors"""
+    _check_frame(w, h, up, prec, 0.2, "noise", cc=cc, use_static=False, expect_static=0)
+
+
+def test_dc_quirk_is_exercised():
+    """white noise has a large (ky=H/2, kx=0) term: dropping the reference's complex-DC leak
+    (vkFFT.h:2108-2131) would move the pre-sharpen plane by >> 1e-5."""
+    w, h = 64, 32
+    plan = vo.make_plan(w, h, 2.0)
+    x = vo.synthetic_frame("noise", w, h)
+    b = vo.shift_zero_pad(vo.forward_spectrum(x.astype(np.float64)), plan)
+    with_quirk = vo.inverse_plane(b, plan)
+    plain = sf.irfft(sf.ifft(b, axis=-2), n=plan.up_w, axis=-1)
+    assert np.abs(with_quirk - plain).max() * plan.up2 > 1e-4
+    r = eu.frame(x, 2.0, 0, 0.2, plan, use_static=False)
+    assert np.abs(r["pre"] - with_quirk).max() * plan.up2 <= 1e-5
+
+
+def test_sharpen_border_rules():
+    """right neighbour of the last column = first pixel of the next row; row below the last row =
+    zero pad; (upW-1, upH-1) with upW == 2*upH reads the next channel's (0,0)."""
+    w, h = 32, 16  # upW = 64 = 2*upH
+    plan = vo.make_plan(w, h, 2.0)
+    rng = np.random.default_rng(5)
+    pre = np.zeros(3 * plan.pre_plane_stride + plan.up_w + 8, np.float32)
+    for c in range(3):
+        pre[c * plan.pre_plane_stride: c * plan.pre_plane_stride + plan.up_w * plan.up_h] = \
+            rng.random(plan.up_w * plan.up_h, dtype=np.float32) / 4
+    out = np.zeros((3, plan.up_h, plan.up_w), np.float32)
+    rc = eu.lib().b2r_emu_sharpen(w, h, 2.0, 0, 0.2, plan.up2, pre.ctypes.data, out.ctypes.data)
+    assert rc == 0
+    ref = vo.sharpen(eu.unpack_pre(pre, plan), plan, 0.2, 0)
+    assert np.array_equal(ref.view(np.uint32), out.view(np.uint32))

@@ -1,0 +1,108 @@
+"""The oracle against the reference's golden vectors and against itself (CPU only)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import scipy.fft as sf
+
+from oracle import vkresample_oracle as vo
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SAMPLES = "/root/reference/samples"
+
+
+def test_pin_record_says_pinned():
+    """the committed record of oracle/pin_goldens.py: every golden byte within 1 LSB, >= 99.99 %
+    identical, nothing further off"""
+    rec = json.load(open(os.path.join(HERE, "golden", "pin_record.json")))
+    assert len(rec["pairs"]) == 2
+    for src, p in rec["pairs"].items():
+        for k in ("float64", "float32"):
+            assert p[k]["max_abs_lsb"] <= 1 and p[k]["n_worse"] == 0
+            assert p[k]["frac_equal"] > 0.9999, (src, k, p[k]["frac_equal"])
+
+
+def test_golden_strips_fixture():
+    """derived fixture: six rows of each golden output vs the oracle's rows stored beside them"""
+    z = np.load(os.path.join(HERE, "golden", "golden_strips.npz"))
+    for dst in ("FFT_upscaled.png", "FFT_upscaled_2.png"):
+        g, o = z[dst + ":gold"].astype(int), z[dst + ":oracle64"].astype(int)
+        d = np.abs(g - o)
+        d = np.minimum(d, 256 - d)
+        assert d.max() <= 1 and (d == 0).mean() > 0.999
+
+
+@pytest.mark.skipif(not os.path.isdir(SAMPLES), reason="reference samples only exist in the authoring container")
+def test_goldens_in_place():
+    """full re-run of the pin on the first golden pair (README.md:55: -i no_upscaling.png -u 2)"""
+    from PIL import Image
+    inp = np.asarray(Image.open(os.path.join(SAMPLES, "no_upscaling.png")).convert("RGB"))
+    gold = np.asarray(Image.open(os.path.join(SAMPLES, "FFT_upscaled.png")).convert("RGB"))
+    out = vo.upscale_u8(inp, 2.0, 0.2, 0, dtype=np.float64, workers=os.cpu_count())
+    d = np.abs(out.astype(np.int16) - gold.astype(np.int16))
+    d = np.minimum(d, 256 - d)
+    assert d.max() <= 1
+    assert (d == 0).mean() > 0.9999
+    rec = json.load(open(os.path.join(HERE, "golden", "pin_record.json")))
+    assert hashlib.sha256(out.tobytes()).hexdigest() == rec["pairs"]["no_upscaling.png"]["float64"]["oracle_sha256"]
+
+
+def test_plan_geometry_matches_reference_formulas():
+    p = vo.make_plan(2048, 1024, 2.0)
+    assert (p.up_w, p.up_h, p.zp_left_y, p.zp_right_y) == (4096, 2048, 512, 1536)
+    assert p.in_plane_stride == 2050 * 1024 and p.pre_plane_stride == 4098 * 2048
+    p = vo.make_plan(1920, 1080, 1.5)
+    assert (p.up_w, p.up_h, p.zp_left_y, p.zp_right_y) == (2880, 1620, 540, 1080)
+    assert p.up2 == 2.25
+
+
+def test_interpolation_property():
+    """a band-limited image is reproduced on the original grid points (before the sharpen)"""
+    w, h = 32, 16
+    yy, xx = np.mgrid[0:h, 0:w]
+    x = np.stack([0.5 + 0.3 * np.cos(2 * np.pi * (3 * xx / w + 2 * yy / h + c / 3)) for c in range(3)])
+    plan = vo.make_plan(w, h, 2.0)
+    pre = vo.pre_sharpen(x.astype(np.float32), plan)
+    assert np.abs(pre[:, ::2, ::2] * 4 - x).max() < 1e-6
+
+
+def test_linearity_of_pre_sharpen():
+    w, h = 48, 20
+    plan = vo.make_plan(w, h, 2.0)
+    a, b = vo.synthetic_frame("noise", w, h, 1), vo.synthetic_frame("noise", w, h, 2)
+    pa, pb = vo.pre_sharpen(a, plan), vo.pre_sharpen(b, plan)
+    pab = vo.pre_sharpen((a + b).astype(np.float32), plan)
+    assert np.abs(pab - (pa + pb)).max() < 2e-6
+
+
+def test_dc_quirk_sign():
+    """the (ky=H/2, kx=0) term vanishes from the reference's output for up=2 (see inverse_plane)"""
+    w, h = 16, 8
+    x = np.zeros((3, h, w), np.float32)
+    x[:, ::2, :] = 1.0  # only DC and the (H/2, 0) term are non-zero
+    plan = vo.make_plan(w, h, 2.0)
+    pre = vo.pre_sharpen(x, plan).astype(np.float64) * 4
+    assert np.abs(pre - 0.5).max() < 1e-6          # reference: constant 0.5
+    b = vo.shift_zero_pad(vo.forward_spectrum(x.astype(np.float64)), plan)
+    plain = sf.irfft(sf.ifft(b, axis=-2), n=plan.up_w, axis=-1) * 4
+    assert np.abs(plain - 0.5).max() > 0.4           # a plain irfft keeps the oscillation
+
+
+def test_sharpen_identity_on_flat_and_quantiser():
+    plan = vo.make_plan(8, 8, 2.0)
+    pre = np.full((3, 16, 16), 0.125, np.float32)
+    out = vo.sharpen(pre, plan, 0.2, 0)
+    assert np.allclose(out[:, 1:-1, 1:-1], 0.5, atol=1e-6)
+    q = vo.quantise(np.array([[[0.0, 0.5, 1.0, -0.001, -1.2 / 255, 1.004]]] * 3, np.float32))
+    assert q[0, :, 0].tolist() == [0, 127, 255, 0, 255, 0]
+
+
+def test_fp16_mode_within_tolerance_of_fp64():
+    w, h = 64, 32
+    x = vo.synthetic_frame("smooth", w, h).astype(np.float16)
+    o16 = vo.upscale_frame(x, 2.0, 0.2, 2, dtype=np.float32)
+    o64 = vo.upscale_frame(x, 2.0, 0.2, 2, dtype=np.float64)
+    assert o16.dtype == np.float16
+    assert np.abs(o16.astype(np.float64) - o64)[:, :-1].max() < 1e-2

@@ -1,0 +1,464 @@
+// b2r_api.cu -- C-ABI (include/b2resample.h) and host runtime of the frame pipeline:
+// device buffers, stream, events, CUDA graph of the per-frame kernel sequence.
+//
+// Replaces, call for call, the Vulkan side of launchResample (VkResample.cpp:1280-1780):
+//   plan create   <- configuration + allocateFFTBuffer x3 + initializeVulkanFFT x2 + createShiftApp
+//                    + createSharpenApp                       (:1409-1617)
+//   upload        <- transferDataFromCPU                      (:1688, def :385-429)
+//   execute       <- performVulkanUpscale                     (:1692, def :1249-1279)
+//   download      <- transferDataToCPU                        (:1697-1700, def :430-473)
+//   destroy       <- deleteVulkanFFT / deleteShiftApp / vkDestroy*   (:1762-1778)
+// The reference records `numIter` copies of its 23 dispatches into one command buffer and times
+// submit -> fence; here one frame is a CUDA graph of 4 kernels, replayed numIter times between two
+// events on the plan's stream.
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/b2resample.h"
+#include "b2r_launch.h"
+#include "b2r_plan.h"
+
+using namespace b2r;
+
+namespace {
+thread_local std::string g_err;
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CU(call)                                                                                  \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(B2R_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+float literal_f(float v) {  // value of the "%f" text the reference pastes into its GLSL (VkResample.cpp:893-920)
+    char t[64];
+    snprintf(t, sizeof t, "%f", (double)v);
+    return strtof(t, nullptr);
+}
+int env_int(const char* name, int dflt) {
+    const char* s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+}  // namespace
+
+struct b2r_plan {
+    int device = 0;
+    uint32_t flags = 0;
+    Geometry g;
+    HostFft fw, fh, fuh, fuw;  // W (R2C rows), H (fwd cols), upH (inv cols), upW (C2R rows)
+    RowImpl k_r2c, k_c2r;      // resolved kernels (static schedule or dynamic fallback)
+    ColImpl k_cols;
+    FrameDims dm{};
+    void* d_in = nullptr;
+    void* d_pre = nullptr;
+    void* d_out = nullptr;
+    float2* d_spec1 = nullptr;
+    float2* d_spec2 = nullptr;
+    float2* d_tw = nullptr;
+    FftDesc* d_fd = nullptr;   // 4 descriptors for the dynamic kernels: W, H, upH, upW
+    const float2 *tw_w = nullptr, *tw_h = nullptr, *tw_uh = nullptr, *tw_uw = nullptr;
+    size_t device_bytes = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    uint64_t launches = 0;
+    int kernels_per_frame = 4;
+};
+
+namespace {
+
+int launch_sharpen(b2r_plan* p, cudaStream_t s, void* d_out = nullptr) {
+    SharpenArgs a{p->d_pre, d_out ? d_out : p->d_out, p->dm, p->g.precision};
+    CU(launch_sharpen_kernel(s, a));
+    return B2R_SUCCESS;
+}
+
+// The per-frame sequence: K1 -> fused columns -> K7 -> K8 (performVulkanUpscale body, :1260-1269)
+// ev (optional, 5 events): recorded before K1 and after each kernel for per-kernel timing.
+int launch_frame(b2r_plan* p, cudaStream_t s, const void* d_in = nullptr, void* d_out = nullptr,
+                 cudaEvent_t* ev = nullptr) {
+    const Geometry& g = p->g;
+    if (ev) CU(cudaEventRecord(ev[0], s));
+    R2cArgs a1{d_in ? d_in : p->d_in, p->d_spec1, p->tw_w, p->d_fd + 0, p->dm, g.precision};
+    CU(p->k_r2c.r2c(s, a1, p->k_r2c.sched.threads, p->k_r2c.smem));
+    if (ev) CU(cudaEventRecord(ev[1], s));
+    ColsArgs a2{p->d_spec1, p->d_spec2, p->tw_h, p->tw_uh, p->d_fd + 1, p->d_fd + 2, p->dm, 1.0f / (float)g.up_h};
+    CU(p->k_cols.launch(s, a2, p->k_cols.inv.threads, p->k_cols.smem));
+    if (ev) CU(cudaEventRecord(ev[2], s));
+    C2rArgs a3{p->d_spec2, p->d_pre, p->tw_uw, p->d_fd + 3, p->dm, g.precision, 1.0f / (float)g.up_w};
+    CU(p->k_c2r.c2r(s, a3, p->k_c2r.sched.threads, p->k_c2r.smem));
+    if (ev) CU(cudaEventRecord(ev[3], s));
+    int rc = launch_sharpen(p, s, d_out);
+    if (rc) return rc;
+    if (ev) CU(cudaEventRecord(ev[4], s));
+    return B2R_SUCCESS;
+}
+
+int run_frame(b2r_plan* p) {
+    if (p->graph_exec) {
+        CU(cudaGraphLaunch(p->graph_exec, p->stream));
+    } else {
+        int rc = launch_frame(p, p->stream);
+        if (rc) return rc;
+    }
+    p->launches += p->kernels_per_frame;
+    return B2R_SUCCESS;
+}
+
+void sched_from(const HostFft& f, Schedule* sc) {
+    sc->n = f.desc.n; sc->nst = f.desc.nstages; sc->threads = f.desc.threads;
+    for (int s = 0; s < f.desc.nstages; ++s) sc->radices[s] = f.desc.st[s].radix;
+}
+
+int build(b2r_plan* p) {
+    Geometry& g = p->g;
+    std::string err;
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, p->device));
+    const size_t smem_max = prop.sharedMemPerBlockOptin;
+    const bool force_dyn = env_int("B2R_FORCE_DYNAMIC", 0) != 0;
+
+    // ---- resolve kernels: static schedule when the size was instantiated, else dynamic
+    if (!force_dyn && find_static_r2c(g.w, &p->k_r2c)) {
+        build_fft(g.w, p->k_r2c.sched.radices, p->k_r2c.sched.nst, p->k_r2c.sched.threads, &p->fw);
+    } else {
+        if (!schedule_fft(g.w, &p->fw, &err)) return fail(B2R_ERR_UNSUPPORTED, "%s", err.c_str());
+        get_dynamic_r2c(&p->k_r2c);
+        sched_from(p->fw, &p->k_r2c.sched);
+        p->k_r2c.smem = (size_t)p->k_r2c.ppb * smem_padded_len(g.w) * sizeof(float2);
+    }
+    if (!force_dyn && find_static_c2r(g.up_w, &p->k_c2r)) {
+        build_fft(g.up_w, p->k_c2r.sched.radices, p->k_c2r.sched.nst, p->k_c2r.sched.threads, &p->fuw);
+    } else {
+        if (!schedule_fft(g.up_w, &p->fuw, &err)) return fail(B2R_ERR_UNSUPPORTED, "%s", err.c_str());
+        get_dynamic_c2r(&p->k_c2r);
+        sched_from(p->fuw, &p->k_c2r.sched);
+        p->k_c2r.smem = (size_t)p->k_c2r.ppb * smem_padded_len(g.up_w) * sizeof(float2);
+    }
+    if (!force_dyn && find_static_cols(g.h, g.up_h, &p->k_cols)) {
+        build_fft(g.h, p->k_cols.fwd.radices, p->k_cols.fwd.nst, p->k_cols.fwd.threads, &p->fh);
+        build_fft(g.up_h, p->k_cols.inv.radices, p->k_cols.inv.nst, p->k_cols.inv.threads, &p->fuh);
+    } else {
+        if (!schedule_fft(g.h, &p->fh, &err) || !schedule_fft(g.up_h, &p->fuh, &err))
+            return fail(B2R_ERR_UNSUPPORTED, "%s", err.c_str());
+        const int tc = std::max(p->fh.desc.threads, p->fuh.desc.threads);
+        schedule_fft(g.h, &p->fh, &err, tc);
+        schedule_fft(g.up_h, &p->fuh, &err, tc);
+        // column tile: widest of {8,4,2} with <= 512 threads and room for >= 2 CTAs per SM
+        int cc = env_int("B2R_COLS_CC", 0);
+        if (cc != 2 && cc != 4 && cc != 8) {
+            cc = 2;
+            for (int cand : {8, 4})
+                if (cand * tc <= kDynMaxThreads && smem_padded_len(g.up_h * cand) * sizeof(float2) <= 100 * 1024) { cc = cand; break; }
+        }
+        get_dynamic_cols(cc, &p->k_cols);
+        sched_from(p->fh, &p->k_cols.fwd);
+        sched_from(p->fuh, &p->k_cols.inv);
+        p->k_cols.smem = (size_t)smem_padded_len(g.up_h * p->k_cols.cc) * sizeof(float2);
+    }
+    const int lim_c = p->k_cols.is_static ? 1024 : kDynMaxThreads;
+    const int lim_1 = p->k_r2c.is_static ? 1024 : kDynMaxThreads, lim_7 = p->k_c2r.is_static ? 1024 : kDynMaxThreads;
+    if (p->k_cols.cc * p->k_cols.inv.threads > lim_c || p->k_cols.smem > smem_max)
+        return fail(B2R_ERR_UNSUPPORTED, "column transform %d x %d does not fit one CTA (%zu B shared, %d threads)",
+                    g.up_h, p->k_cols.cc, p->k_cols.smem, p->k_cols.cc * p->k_cols.inv.threads);
+    if (p->k_r2c.sched.threads * p->k_r2c.ppb > lim_1 || p->k_c2r.sched.threads * p->k_c2r.ppb > lim_7 ||
+        p->k_r2c.smem > smem_max || p->k_c2r.smem > smem_max)
+        return fail(B2R_ERR_UNSUPPORTED, "row transform %d / %d does not fit one CTA", g.w, g.up_w);
+    CU(p->k_r2c.prepare(p->k_r2c.smem));
+    CU(p->k_c2r.prepare(p->k_c2r.smem));
+    CU(p->k_cols.prepare(p->k_cols.smem));
+
+    // kernel-side dimensions
+    FrameDims& d = p->dm;
+    d.w = g.w; d.h = g.h; d.up_w = g.up_w; d.up_h = g.up_h; d.nx = g.nx; d.spec_stride = g.spec_stride;
+    d.zp_lo = g.zp_lo; d.zp_hi = g.zp_hi; d.neg_shift = g.neg_shift;
+    d.in_plane = g.in_plane; d.pre_plane = g.pre_plane; d.out_plane = g.out_plane;
+    const bool raw = p->flags & B2R_FLAG_NO_SHARPEN_LITERAL_ROUNDING;
+    d.up2 = raw ? g.up2 : literal_f(g.up2);
+    d.sharpen = raw ? g.sharpen : literal_f(g.sharpen);
+
+    // device memory
+    const size_t eb = g.elem_bytes();
+    const size_t b_in = g.input_bytes(), b_pre = g.pre_elems * eb, b_out = g.output_bytes();
+    const size_t b_s1 = g.spec_in_elems() * sizeof(float2), b_s2 = g.spec_out_elems() * sizeof(float2);
+    const size_t n_tw = p->fw.twiddles.size() + p->fh.twiddles.size() + p->fuh.twiddles.size() + p->fuw.twiddles.size();
+    CU(cudaMalloc(&p->d_in, b_in));
+    CU(cudaMalloc(&p->d_pre, b_pre));
+    CU(cudaMalloc(&p->d_out, b_out));
+    CU(cudaMalloc((void**)&p->d_spec1, b_s1));
+    CU(cudaMalloc((void**)&p->d_spec2, b_s2));
+    CU(cudaMalloc((void**)&p->d_tw, (n_tw + 1) * sizeof(float2)));
+    CU(cudaMalloc((void**)&p->d_fd, 4 * sizeof(FftDesc)));
+    p->device_bytes = b_in + b_pre + b_out + b_s1 + b_s2 + (n_tw + 1) * sizeof(float2) + 4 * sizeof(FftDesc);
+    CU(cudaMemset(p->d_in, 0, b_in));
+    CU(cudaMemset(p->d_pre, 0, b_pre));  // the plane pad regions stay zero for the plan's lifetime
+    CU(cudaMemset(p->d_spec1, 0, b_s1));
+    CU(cudaMemset(p->d_spec2, 0, b_s2));
+    const FftDesc descs[4] = {p->fw.desc, p->fh.desc, p->fuh.desc, p->fuw.desc};
+    CU(cudaMemcpy(p->d_fd, descs, sizeof descs, cudaMemcpyHostToDevice));
+    size_t off = 0;
+    auto put = [&](const HostFft& f, const float2** slot) -> int {
+        *slot = p->d_tw + off;
+        if (!f.twiddles.empty())
+            CU(cudaMemcpy(p->d_tw + off, f.twiddles.data(), f.twiddles.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        off += f.twiddles.size();
+        return B2R_SUCCESS;
+    };
+    int rc;
+    if ((rc = put(p->fw, &p->tw_w)) || (rc = put(p->fh, &p->tw_h)) || (rc = put(p->fuh, &p->tw_uh)) ||
+        (rc = put(p->fuw, &p->tw_uw)))
+        return rc;
+
+    CU(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&p->ev0));
+    CU(cudaEventCreate(&p->ev1));
+
+    if (!(p->flags & B2R_FLAG_NO_GRAPH)) {
+        CU(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
+        rc = launch_frame(p, p->stream);
+        cudaError_t e = cudaStreamEndCapture(p->stream, &p->graph);
+        if (rc) return rc;
+        CU(e);
+        CU(cudaGraphInstantiate(&p->graph_exec, p->graph, 0));
+    }
+    CU(cudaStreamSynchronize(p->stream));
+    return B2R_SUCCESS;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b2r_last_error(void) { return g_err.c_str(); }
+const char* b2r_version(void) { return "b2resample 0.1 (sm_100a)"; }
+
+int b2r_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { fail(B2R_ERR_CUDA, "cudaGetDeviceCount failed: %s", cudaGetErrorString(e)); return 0; }
+    return n;
+}
+
+int b2r_device_name(int device, char* buf, size_t buf_len) {
+    if (!buf || !buf_len) return fail(B2R_ERR_INVALID_ARG, "null buffer");
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    snprintf(buf, buf_len, "%s", prop.name);
+    return B2R_SUCCESS;
+}
+
+int b2r_plan_create(b2r_plan** out, int device, uint32_t w, uint32_t h, float upscale, uint32_t precision,
+                    float sharpen, uint32_t flags) {
+    if (!out) return fail(B2R_ERR_INVALID_ARG, "out is null");
+    *out = nullptr;
+    if (precision == 1) return fail(B2R_ERR_UNSUPPORTED, "precision 1 (double) is not supported; use 0 (fp32) or 2 (fp16)");
+    Geometry g;
+    std::string err;
+    if (!make_geometry((int)w, (int)h, upscale, (int)precision, sharpen, &g, &err))
+        return fail(err.find("not of the form") != std::string::npos ? B2R_ERR_UNSUPPORTED : B2R_ERR_INVALID_ARG, "%s", err.c_str());
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(B2R_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= ndev) return fail(B2R_ERR_INVALID_ARG, "device %d out of range [0,%d)", device, ndev);
+    CU(cudaSetDevice(device));
+    b2r_plan* p = new (std::nothrow) b2r_plan();
+    if (!p) return fail(B2R_ERR_NOMEM, "out of host memory");
+    p->device = device; p->flags = flags; p->g = g;
+    int rc = build(p);
+    if (rc) { std::string keep = g_err; b2r_plan_destroy(p); g_err = keep; return rc; }
+    *out = p;
+    return B2R_SUCCESS;
+}
+
+void b2r_plan_destroy(b2r_plan* p) {
+    if (!p) return;
+    cudaSetDevice(p->device);
+    if (p->stream) cudaStreamSynchronize(p->stream);
+    if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
+    if (p->graph) cudaGraphDestroy(p->graph);
+    if (p->ev0) cudaEventDestroy(p->ev0);
+    if (p->ev1) cudaEventDestroy(p->ev1);
+    if (p->stream) cudaStreamDestroy(p->stream);
+    cudaFree(p->d_in); cudaFree(p->d_pre); cudaFree(p->d_out);
+    cudaFree(p->d_spec1); cudaFree(p->d_spec2); cudaFree(p->d_tw); cudaFree(p->d_fd);
+    delete p;
+}
+
+size_t b2r_plan_input_bytes(const b2r_plan* p) { return p ? p->g.input_bytes() : 0; }
+size_t b2r_plan_output_bytes(const b2r_plan* p) { return p ? p->g.output_bytes() : 0; }
+size_t b2r_plan_pre_sharpen_bytes(const b2r_plan* p) { return p ? 3 * p->g.pre_plane * p->g.elem_bytes() : 0; }
+
+int b2r_plan_get_info(const b2r_plan* p, b2r_plan_info* info) {
+    if (!p || !info) return fail(B2R_ERR_INVALID_ARG, "null argument");
+    memset(info, 0, sizeof *info);
+    const Geometry& g = p->g;
+    info->w = g.w; info->h = g.h; info->up_w = g.up_w; info->up_h = g.up_h;
+    info->precision = g.precision; info->upscale = g.upscale; info->sharpen = g.sharpen;
+    info->zeropad_lo_y = g.zp_lo; info->zeropad_hi_y = g.zp_hi;
+    info->spectrum_row_stride = g.spec_stride;
+    info->input_bytes = g.input_bytes(); info->output_bytes = g.output_bytes();
+    info->device_bytes = p->device_bytes;
+    const HostFft* f[4] = {&p->fw, &p->fh, &p->fuh, &p->fuw};
+    for (int i = 0; i < 4; ++i) {
+        info->n_stages[i] = f[i]->desc.nstages;
+        info->threads[i] = f[i]->desc.threads;
+        for (int s = 0; s < f[i]->desc.nstages; ++s) info->radices[i][s] = f[i]->desc.st[s].radix;
+    }
+    info->column_tile = p->k_cols.cc;
+    info->static_kernels = (p->k_r2c.is_static ? 1u : 0u) | (p->k_cols.is_static ? 2u : 0u) | (p->k_c2r.is_static ? 4u : 0u);
+    info->kernels_per_frame = p->kernels_per_frame;
+    return B2R_SUCCESS;
+}
+
+int b2r_upload(b2r_plan* p, const void* host_in) {
+    if (!p || !host_in) return fail(B2R_ERR_INVALID_ARG, "null argument");
+    CU(cudaSetDevice(p->device));
+    CU(cudaMemcpyAsync(p->d_in, host_in, p->g.input_bytes(), cudaMemcpyHostToDevice, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    return B2R_SUCCESS;
+}
+
+int b2r_execute(b2r_plan* p, uint32_t num_iter, double* ms_per_iter) {
+    if (!p || num_iter == 0) return fail(B2R_ERR_INVALID_ARG, "null plan or num_iter == 0");
+    CU(cudaSetDevice(p->device));
+    CU(cudaEventRecord(p->ev0, p->stream));
+    for (uint32_t i = 0; i < num_iter; ++i) {
+        int rc = run_frame(p);
+        if (rc) return rc;
+    }
+    CU(cudaEventRecord(p->ev1, p->stream));
+    CU(cudaEventSynchronize(p->ev1));
+    CU(cudaGetLastError());
+    if (ms_per_iter) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
+        *ms_per_iter = (double)ms / (double)num_iter;
+    }
+    return B2R_SUCCESS;
+}
+
+int b2r_download(b2r_plan* p, void* host_out) {
+    if (!p || !host_out) return fail(B2R_ERR_INVALID_ARG, "null argument");
+    CU(cudaSetDevice(p->device));
+    CU(cudaMemcpyAsync(host_out, p->d_out, p->g.output_bytes(), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    return B2R_SUCCESS;
+}
+
+int b2r_upscale_host(b2r_plan* p, const void* host_in, void* host_out, double* ms_total) {
+    if (!p || !host_in || !host_out) return fail(B2R_ERR_INVALID_ARG, "null argument");
+    CU(cudaSetDevice(p->device));
+    CU(cudaEventRecord(p->ev0, p->stream));
+    CU(cudaMemcpyAsync(p->d_in, host_in, p->g.input_bytes(), cudaMemcpyHostToDevice, p->stream));
+    int rc = run_frame(p);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(host_out, p->d_out, p->g.output_bytes(), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaEventRecord(p->ev1, p->stream));
+    CU(cudaEventSynchronize(p->ev1));
+    if (ms_total) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, p->ev0, p->ev1));
+        *ms_total = ms;
+    }
+    return B2R_SUCCESS;
+}
+
+void* b2r_device_input(b2r_plan* p) { return p ? p->d_in : nullptr; }
+void* b2r_device_output(b2r_plan* p) { return p ? p->d_out : nullptr; }
+void* b2r_plan_stream(b2r_plan* p) { return p ? (void*)p->stream : nullptr; }
+uint64_t b2r_plan_launch_count(const b2r_plan* p) { return p ? p->launches : 0; }
+
+int b2r_download_pre_sharpen(b2r_plan* p, void* host_out) {
+    if (!p || !host_out) return fail(B2R_ERR_INVALID_ARG, "null argument");
+    CU(cudaSetDevice(p->device));
+    CU(cudaMemcpyAsync(host_out, p->d_pre, b2r_plan_pre_sharpen_bytes(p), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    return B2R_SUCCESS;
+}
+
+int b2r_sharpen_host(b2r_plan* p, const void* host_pre, void* host_out) {
+    if (!p || !host_pre || !host_out) return fail(B2R_ERR_INVALID_ARG, "null argument");
+    CU(cudaSetDevice(p->device));
+    CU(cudaMemcpyAsync(p->d_pre, host_pre, b2r_plan_pre_sharpen_bytes(p), cudaMemcpyHostToDevice, p->stream));
+    int rc = launch_sharpen(p, p->stream);
+    if (rc) return rc;
+    p->launches += 1;
+    CU(cudaMemcpyAsync(host_out, p->d_out, p->g.output_bytes(), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    return B2R_SUCCESS;
+}
+
+int b2r_enqueue_device(b2r_plan* p, const void* d_in, void* d_out) {
+    if (!p || !d_in || !d_out) return fail(B2R_ERR_INVALID_ARG, "null argument");
+    CU(cudaSetDevice(p->device));
+    int rc = launch_frame(p, p->stream, d_in, d_out);
+    if (rc) return rc;
+    p->launches += p->kernels_per_frame;
+    return B2R_SUCCESS;
+}
+
+int b2r_timer_start(b2r_plan* p) {
+    if (!p) return fail(B2R_ERR_INVALID_ARG, "null plan");
+    CU(cudaSetDevice(p->device));
+    CU(cudaEventRecord(p->ev0, p->stream));
+    return B2R_SUCCESS;
+}
+
+int b2r_timer_stop(b2r_plan* p, double* ms) {
+    if (!p) return fail(B2R_ERR_INVALID_ARG, "null plan");
+    CU(cudaSetDevice(p->device));
+    CU(cudaEventRecord(p->ev1, p->stream));
+    CU(cudaEventSynchronize(p->ev1));
+    CU(cudaGetLastError());
+    float t = 0.f;
+    CU(cudaEventElapsedTime(&t, p->ev0, p->ev1));
+    if (ms) *ms = t;
+    return B2R_SUCCESS;
+}
+
+int b2r_profile_kernels(b2r_plan* p, uint32_t num_iter, double* ms_per_kernel) {
+    if (!p || !num_iter || !ms_per_kernel) return fail(B2R_ERR_INVALID_ARG, "null argument");
+    CU(cudaSetDevice(p->device));
+    std::vector<cudaEvent_t> ev(5 * (size_t)num_iter);
+    for (auto& e : ev) CU(cudaEventCreate(&e));
+    for (uint32_t i = 0; i < num_iter; ++i) {
+        int rc = launch_frame(p, p->stream, nullptr, nullptr, &ev[5 * (size_t)i]);
+        if (rc) return rc;
+        p->launches += p->kernels_per_frame;
+    }
+    CU(cudaStreamSynchronize(p->stream));
+    for (int k = 0; k < 4; ++k) ms_per_kernel[k] = 0.0;
+    for (uint32_t i = 0; i < num_iter; ++i)
+        for (int k = 0; k < 4; ++k) {
+            float t = 0.f;
+            CU(cudaEventElapsedTime(&t, ev[5 * (size_t)i + k], ev[5 * (size_t)i + k + 1]));
+            ms_per_kernel[k] += (double)t / num_iter;
+        }
+    for (auto& e : ev) cudaEventDestroy(e);
+    return B2R_SUCCESS;
+}
+
+int b2r_synchronize(b2r_plan* p) {
+    if (!p) return fail(B2R_ERR_INVALID_ARG, "null plan");
+    CU(cudaSetDevice(p->device));
+    CU(cudaStreamSynchronize(p->stream));
+    return B2R_SUCCESS;
+}
+
+}  // extern "C"

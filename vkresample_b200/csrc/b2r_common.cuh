@@ -1,0 +1,63 @@
+// b2r_common.cuh -- compiler glue shared by every device header.
+//
+// Two build modes:
+//   * nvcc, -gencode arch=compute_100a,code=sm_100a  : the product (libb2resample.so).
+//   * g++ with -DB2R_HOST_EMU                         : tests/emu only.  The same kernel source is
+//     run by OS threads (one per CUDA thread of a CTA, std::barrier for __syncthreads) so that the
+//     index arithmetic of every kernel can be checked against the oracle in the GPU-less authoring
+//     container.  It is test infrastructure; the product never links it and has no CPU fallback.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <cuda_fp16.h>
+#include <cstdint>
+#include <type_traits>
+
+#if defined(B2R_HOST_EMU)
+#include <cmath>
+namespace b2r_emu {
+struct Ctx {
+    unsigned tid_x, tid_y, bid_x, bid_y, bid_z, bdim_x, bdim_y, gdim_x, gdim_y, gdim_z;
+    unsigned char* smem;
+    void (*sync)(void*);
+    void* sync_arg;
+};
+extern thread_local Ctx g_ctx;
+}  // namespace b2r_emu
+#define B2R_HD inline
+#define B2R_DEV inline
+#define B2R_KERNEL inline void
+#define B2R_TID_X (b2r_emu::g_ctx.tid_x)
+#define B2R_TID_Y (b2r_emu::g_ctx.tid_y)
+#define B2R_BID_X (b2r_emu::g_ctx.bid_x)
+#define B2R_BID_Y (b2r_emu::g_ctx.bid_y)
+#define B2R_BID_Z (b2r_emu::g_ctx.bid_z)
+#define B2R_BDIM_X (b2r_emu::g_ctx.bdim_x)
+#define B2R_BDIM_Y (b2r_emu::g_ctx.bdim_y)
+#define B2R_GDIM_X (b2r_emu::g_ctx.gdim_x)
+#define B2R_SYNC() (b2r_emu::g_ctx.sync(b2r_emu::g_ctx.sync_arg))
+#define B2R_SMEM(T) (reinterpret_cast<T*>(b2r_emu::g_ctx.smem))
+#define B2R_LDG(p) (*(p))
+#define B2R_LAUNCH_BOUNDS(t, b)
+#else
+#define B2R_HD __host__ __device__ __forceinline__
+#define B2R_DEV __device__ __forceinline__
+#define B2R_KERNEL __global__ void
+#define B2R_TID_X (threadIdx.x)
+#define B2R_TID_Y (threadIdx.y)
+#define B2R_BID_X (blockIdx.x)
+#define B2R_BID_Y (blockIdx.y)
+#define B2R_BID_Z (blockIdx.z)
+#define B2R_BDIM_X (blockDim.x)
+#define B2R_BDIM_Y (blockDim.y)
+#define B2R_GDIM_X (gridDim.x)
+#define B2R_SYNC() __syncthreads()
+#define B2R_SMEM(T) (reinterpret_cast<T*>(b2r_dyn_smem))
+#if defined(__CUDA_ARCH__)
+#define B2R_LDG(p) __ldg(p)
+#else
+#define B2R_LDG(p) (*(p))
+#endif
+#define B2R_LAUNCH_BOUNDS(t, b) __launch_bounds__(t, b)
+extern __shared__ __align__(16) unsigned char b2r_dyn_smem[];
+#endif

@@ -1,0 +1,67 @@
+// b2r_launch.h -- host-side launch interface between the plan runtime (b2r_api.cu) and the kernel
+// translation units.  Two families implement it:
+//   * static  (b2r_static_rows.cu / b2r_static_cols.cu): schedules instantiated at build time for
+//     the sizes in b2r_static_sizes.h -- every stride / count is an immediate in the SASS;
+//   * dynamic (b2r_dynamic.cu): one kernel per kind that reads its schedule from a device-resident
+//     FftDesc, for any 2^a 3^b 5^c 7^d size (what the reference gets from JIT-compiling GLSL,
+//     vkFFT.h:4495-4642, we get from a runtime radix dispatch).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "b2r_fft.cuh"
+#include "b2r_kernels.cuh"
+
+namespace b2r {
+
+struct R2cArgs {
+    const void* in; float2* spec; const float2* tw; const FftDesc* dfd; FrameDims dm; int precision;
+};
+struct ColsArgs {
+    const float2* in; float2* out; const float2 *tw_f, *tw_i; const FftDesc *dfd_f, *dfd_i; FrameDims dm; float scale;
+};
+struct C2rArgs {
+    const float2* spec; void* pre; const float2* tw; const FftDesc* dfd; FrameDims dm; int precision; float scale;
+};
+struct SharpenArgs {
+    const void* pre; void* out; FrameDims dm; int precision;
+};
+
+struct Schedule {      // radix list + cooperating threads of one transform
+    int n = 0, nst = 0, threads = 0;
+    int radices[kMaxStages] = {};
+};
+
+struct RowImpl {       // K1 or K7 resolved for one size
+    const char* name = nullptr;
+    bool is_static = false;
+    Schedule sched;
+    int ppb = 1;               // row pairs per CTA
+    size_t smem = 0;
+    cudaError_t (*prepare)(size_t smem) = nullptr;   // per-device function attributes
+    cudaError_t (*r2c)(cudaStream_t, const R2cArgs&, int ppb, size_t smem) = nullptr;
+    cudaError_t (*c2r)(cudaStream_t, const C2rArgs&, int ppb, size_t smem) = nullptr;
+};
+
+struct ColImpl {       // fused column kernel resolved for one (H, upH) pair
+    const char* name = nullptr;
+    bool is_static = false;
+    Schedule fwd, inv;         // same thread count
+    int cc = 4;                // spectrum columns per CTA
+    size_t smem = 0;
+    cudaError_t (*prepare)(size_t smem) = nullptr;
+    cudaError_t (*launch)(cudaStream_t, const ColsArgs&, int threads, size_t smem) = nullptr;
+};
+
+// static registries: return false when the size was not instantiated at build time
+bool find_static_r2c(int n, RowImpl* out);
+bool find_static_c2r(int n, RowImpl* out);
+bool find_static_cols(int h, int up_h, ColImpl* out);
+// dynamic fallbacks (always succeed for schedulable sizes); cc in {2,4,8}
+void get_dynamic_r2c(RowImpl* out);
+void get_dynamic_c2r(RowImpl* out);
+void get_dynamic_cols(int cc, ColImpl* out);
+
+cudaError_t launch_sharpen_kernel(cudaStream_t s, const SharpenArgs& a);
+
+}  // namespace b2r

@@ -1,0 +1,39 @@
+// b2r_static_cols.cu -- fused column kernel (K2..K6) instantiated for the (H, upH) pairs in
+// b2r_static_sizes.h.
+#include "b2r_launch.h"
+#include "b2r_static_sizes.h"
+
+namespace b2r {
+namespace {
+template <class PF, class PI, int CC> cudaError_t prep(size_t smem) {
+    if (smem <= 48 * 1024) return cudaSuccess;
+    return cudaFuncSetAttribute(k_cols<PF, PI, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+template <class PF, class PI, int CC> cudaError_t run(cudaStream_t s, const ColsArgs& a, int, size_t smem) {
+    dim3 block(PI::kT * CC), grid((a.dm.nx + CC - 1) / CC, 3);
+    k_cols<PF, PI, CC><<<grid, block, smem, s>>>(a.in, a.out, a.tw_f, a.tw_i, PF{}, PI{}, a.dm, a.scale);
+    return cudaGetLastError();
+}
+template <class P> void sched_of(Schedule* sc) {
+    sc->n = P::kN; sc->nst = P::kStages; sc->threads = P::kT;
+    for (int s = 0; s < P::kStages; ++s) sc->radices[s] = P::radix(s);
+}
+template <class PF, class PI, int CC> void fill(ColImpl* o, const char* name) {
+    static_assert(PF::kT == PI::kT, "forward and inverse column schedules must share the thread count");
+    *o = ColImpl{};
+    o->name = name; o->is_static = true; o->cc = CC;
+    sched_of<PF>(&o->fwd); sched_of<PI>(&o->inv);
+    o->smem = (size_t)smem_padded_len(PI::kN * CC) * sizeof(float2);
+    o->prepare = &prep<PF, PI, CC>;
+    o->launch = &run<PF, PI, CC>;
+}
+}  // namespace
+
+bool find_static_cols(int h, int up_h, ColImpl* out) {
+#define X(H, UPH, CC, PF, PI) \
+    if (h == H && up_h == UPH) { fill<PF, PI, CC>(out, "cols<" #H "->" #UPH ">"); return true; }
+    B2R_STATIC_COLS(X)
+#undef X
+    return false;
+}
+}  // namespace b2r
