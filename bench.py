@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the FFT-upscale hot path (BASELINE.json: frames/s,
+2048x1024 -> 4096x2048 2x upscale, fp32, at 1/2/4/8 B200; HBM GB/s vs peak).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's algorithm on host cores
+
+One "step" = FRAMES_PER_STEP frames pushed through the whole pipeline (R2C rows -> fused column
+FFT/shift/zero-pad/inverse -> C2R rows -> sharpen).  `value` is measured with the frames already
+resident in HBM (a ring of distinct device frames so that no iteration can reuse another's lines
+in L2); `e2e` goes through the C-ABI with pinned HOST buffers, H2D and D2H inside the timed region.
+N > 1: launched by torchrun, one rank per GPU, whole frames sharded across ranks, no collective on
+the data path -- torch.distributed is only the barrier and the max-over-ranks.
+The reference arm cannot run the Vulkan binary (no Vulkan loader / lavapipe in the image, see
+DESIGN.md): it times the CPU oracle port (oracle/, pocketfft + numpy, all host threads).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+CONFIGS = {
+    # name: (W, H, upscale, precision, sharpen)
+    "c1": (256, 128, 2.0, 0, 0.2),
+    "c2": (2048, 1024, 2.0, 0, 0.2),
+    "c3": (1920, 1080, 2.0, 2, 0.2),
+    "c4": (2048, 1024, 2.0, 2, 0.2),
+    "c5": (3840, 2160, 2.0, 0, 0.2),
+}
+METRIC = "frames/s 2048x1024->4096x2048 2x upscale"
+UNIT = "frames/s"
+
+
+def workload_name(cfg):
+    w, h, up, prec, s = CONFIGS[cfg]
+    return f"{cfg}: {w}x{h}->{int(up * w)}x{int(up * h)} {'fp16' if prec == 2 else 'fp32'} {up:g}x upscale + sharpen {s}"
+
+
+def peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def kernel_algorithmic_bytes(w, h, up_w, up_h, elem):
+    """compulsory HBM bytes of each kernel per frame: what it must read once
+    plus what it must write once"""
+    nx = w // 2 + 1
+    b_in, b_s1, b_s2 = 3 * h * w * elem, 3 * h * nx * 8, 3 * up_h * nx * 8
+    b_pre = b_out = 3 * up_h * up_w * elem
+    return {"r2c_rows": b_in + b_s1, "cols": b_s1 + b_s2, "c2r_rows": b_s2 + b_pre, "sharpen": b_pre + b_out,
+            "frame": b_in + b_out}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------ CPU arms
+def cpu_frames_per_s(cfg, n_frames, workers):
+    """the oracle port on host cores (checker timed as the CPU baseline; never the product path)"""
+    from oracle import vkresample_oracle as vo
+    w, h, up, prec, s = CONFIGS[cfg]
+    x = vo.synthetic_frame("noise", w, h)
+    if prec == 2:
+        x = x.astype(np.float16)
+    vo.upscale_frame(x, up, s, prec, dtype=np.float32, workers=workers)  # warm pocketfft plans
+    t0 = time.perf_counter()
+    for _ in range(n_frames):
+        vo.upscale_frame(x, up, s, prec, dtype=np.float32, workers=workers)
+    return n_frames / (time.perf_counter() - t0)
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    from oracle import vkresample_oracle as vo
+    w, h, up, prec, s = CONFIGS[args.config]
+    x = vo.synthetic_frame("noise", w, h)
+    if prec == 2:
+        x = x.astype(np.float16)
+    for _ in range(min(args.warmup, 2)):
+        vo.upscale_frame(x, up, s, prec, dtype=np.float32, workers=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        vo.upscale_frame(x, up, s, prec, dtype=np.float32, workers=cores)
+    dt = time.perf_counter() - t0
+    v = args.steps / dt
+    sample = f"{args.steps} steps x 1 frame of {workload_name(args.config)} (oracle port: pocketfft complex64 + numpy sharpen)"
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args.config), "frames_per_step": 1,
+                       "note": "reference Vulkan binary not runnable here (no Vulkan loader/lavapipe); CPU oracle port timed instead"},
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------ GPU arm
+def run_b200(args):
+    import torch
+    import vkresample_b200 as vb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if not torch.cuda.is_available() or vb.device_count() < 1:
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback): " + vb.load_library().b2r_last_error().decode())
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+
+    w, h, up, prec, s = CONFIGS[args.config]
+    F = args.frames_per_step
+    plan = vb.Plan(w, h, up, prec, s, device=local)
+    elem = 2 if prec == 2 else 4
+    np_dt = np.float16 if prec == 2 else np.float32
+
+    # ring of distinct device-resident frames: 2x the L2 (126 MB) worth of inputs + their outputs
+    ring = max(2, min(args.ring, 16))
+    rng = np.random.default_rng(1234 + rank)
+    d_in, d_out = [], []
+    for i in range(ring):
+        x = rng.random((3, h, w), dtype=np.float32).astype(np_dt)
+        host = plan.pack_input(x)
+        d_in.append(torch.from_numpy(host.view(np.uint8)).to(dev))
+        d_out.append(torch.empty(plan.output_bytes, dtype=torch.uint8, device=dev))
+    torch.cuda.synchronize()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(i0):
+        for f in range(F):
+            k = (i0 + f) % ring
+            plan.enqueue_device(d_in[k].data_ptr(), d_out[k].data_ptr())
+
+    for i in range(args.warmup):
+        step(i * F)
+    plan.synchronize()
+
+    sampler = ClockSampler(local)
+    launches0 = plan.launch_count
+    barrier()
+    sampler.start()
+    t_wall0 = time.perf_counter()
+    plan.timer_start()
+    for i in range(args.steps):
+        step(i * F)
+    ms = plan.timer_stop()          # CUDA events on the launching stream
+    t_wall = time.perf_counter() - t_wall0
+    clocks = sampler.stop()
+    barrier()
+    launches = plan.launch_count - launches0
+
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * args.steps * F / (ms_max * 1e-3)
+
+    # ---- end to end through the C-ABI with pinned host buffers (H2D + frame + D2H per frame)
+    e_frames = max(4, min(F, 16))
+    h_in = [torch.from_numpy(plan.pack_input(rng.random((3, h, w), dtype=np.float32).astype(np_dt)).view(np.uint8)).pin_memory()
+            for _ in range(2)]
+    h_out = [torch.empty(plan.output_bytes, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    for i in range(2):
+        plan.upscale_host(h_in[i].data_ptr(), h_out[i].data_ptr())
+    e_steps = max(1, min(args.steps, 5))
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e_steps * e_frames):
+        plan.upscale_host(h_in[i % 2].data_ptr(), h_out[i % 2].data_ptr())
+    plan.synchronize()
+    e_dt = time.perf_counter() - t0
+    te = torch.tensor([e_dt], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * e_steps * e_frames / float(te.item())
+    result_checksum = float(np.frombuffer(h_out[0].numpy().tobytes()[:4096], dtype=np_dt).astype(np.float64).sum())
+
+    # ---- roofline of the dominant kernel (separate pass, events between kernels, same workload)
+    pk = plan.profile_kernels(20)
+    alg = kernel_algorithmic_bytes(w, h, plan.up_w, plan.up_h, elem)
+    dom = max(pk, key=pk.get)
+    peak, peak_src = peaks()
+    achieved = alg[dom] / (pk[dom] * 1e-3) / 1e9
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        traffic = tj.get(args.config, {}).get(dom)
+    except Exception:
+        pass
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg[dom],
+                "kernel_us": {k: round(v * 1e3, 2) for k, v in pk.items()},
+                "kernel_frac": {k: round(alg[k] / (v * 1e-3) / 1e9 / peak, 4) for k, v in pk.items()},
+                "frame_algorithmic_gbs": alg["frame"] * value / world / 1e9,
+                "frame_frac": alg["frame"] * value / world / 1e9 / peak}
+
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cores = os.cpu_count() or 1
+            n = 4 if args.config != "c5" else 2
+            v = cpu_frames_per_s(args.config, n, cores)
+            cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                   "sample": f"{n} frames of {workload_name(args.config)} (oracle port: pocketfft complex64 + numpy sharpen, {cores} threads)"}
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if prec == 0 else "f16 storage / f32 FFT",
+                "data": "synthetic",
+                "config": {"workload": workload_name(args.config), "frames_per_step": F, "frames_per_gpu_per_step": F,
+                           "parallelism": f"frames sharded over {world} GPU(s), no collective",
+                           "l2": f"ring of {ring} distinct device-resident frames ({ring * (plan.input_bytes + plan.output_bytes) >> 20} MiB in+out, "
+                                 f"~{(alg['r2c_rows'] + alg['cols'] + alg['c2r_rows'] + alg['sharpen']) >> 20} MiB touched per frame) > 126 MB L2",
+                           "radix_schedule": plan.radix_schedule(), "column_tile": int(plan.info.column_tile),
+                           "static_kernels": int(plan.info.static_kernels)},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e_frames * plan.input_bytes,
+                        "d2h_bytes_per_step": e_frames * plan.output_bytes, "frames_per_step": e_frames,
+                        "steps": e_steps, "api": "b2r_upscale_host (pinned host in -> pinned host out)",
+                        "checksum": result_checksum},
+                "gpu_launches": int(launches), "wall_s_timed_region": t_wall,
+                "roofline": roofline, "clocks": clocks}
+        if cpu:
+            line["cpu_baseline"] = cpu
+        print(json.dumps(line))
+    plan.close()
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--frames-per-step", type=int, default=32)
+    ap.add_argument("--ring", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -202,8 +202,44 @@ def _flat_with_pad(pre: np.ndarray, plan: FramePlan) -> np.ndarray:
     return flat
 
 
+def _literal(v) -> np.float32:
+    """The value of a float pasted into the GLSL source with "%f" (6 decimals) and parsed back as
+    a float literal (VkResample.cpp:893-920: ``app->upscale``, ``app->sharpenCoeff``)."""
+    return np.float32(float("%f" % float(np.float32(v))))
+
+
+def _sharpen_rows(t_all, base, up_w, up_h, y0, y1, s, dt, out_ch):
+    """rows [y0, y1) of one channel; t_all = clamped magnitudes of the whole flat buffer"""
+    ya = max(y0 - 1, 0)
+    n_rows = (y1 + 1) - ya                                   # rows ya .. y1 inclusive
+    e0 = t_all[base + ya * up_w: base + (ya + n_rows) * up_w].reshape(n_rows, up_w)           # X = x
+    ep = t_all[base + ya * up_w + 1: base + (ya + n_rows) * up_w + 1].reshape(n_rows, up_w)   # X = x+1 (flat)
+    em = np.empty_like(e0)
+    em[:, 1:] = e0[:, :-1]
+    em[:, 0] = e0[:, 0]                                                                         # X = max(x-1,0)
+    ys = np.arange(y0, y1)
+    r_m = np.maximum(ys - 1, 0) - ya
+    r_0 = ys - ya
+    r_p = ys + 1 - ya
+    l0, l1, l2 = em[r_m], e0[r_m], ep[r_m]
+    l3, l4, l5 = em[r_0], e0[r_0], ep[r_0]
+    l6, l7, l8 = em[r_p], e0[r_p], ep[r_p]
+    mn0 = np.minimum(l1, np.minimum(l3, np.minimum(l4, np.minimum(l5, l7))))
+    mn1 = np.minimum(mn0, np.minimum(l0, np.minimum(l2, np.minimum(l6, l8))))
+    mx0 = np.maximum(l1, np.maximum(l3, np.maximum(l4, np.maximum(l5, l7))))
+    mx1 = np.maximum(mx0, np.maximum(l0, np.maximum(l2, np.maximum(l6, l8))))
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        minlen = dt(0.5) * (mn0 + mn1)
+        maxlen = dt(0.5) * (mx0 + mx1)
+        minlen = minlen / (dt(1.0) - minlen)
+        maxlen = (dt(1.0) - maxlen) / maxlen
+        scale = np.where(minlen < maxlen, minlen, maxlen)
+        scale = -s * np.sqrt(scale)
+        out_ch[y0:y1] = (l4 + scale * (((l1 + l3) + l5) + l7)) / (dt(1.0) + scale * dt(4.0))
+
+
 def sharpen(pre: np.ndarray, plan: FramePlan, sharpen_const: float = 0.2,
-            precision: int = 0, dtype=None) -> np.ndarray:
+            precision: int = 0, dtype=None, workers=None) -> np.ndarray:
     """FidelityFX-CAS-like 3x3 sharpen, R2C branch.  VkResample.cpp:849-923, strides
     :1564-1617, launch :1202-1219.
 
@@ -214,7 +250,8 @@ def sharpen(pre: np.ndarray, plan: FramePlan, sharpen_const: float = 0.2,
 
     ``dtype``: arithmetic type.  Default: float16 for precision 2 (the shader is
     generated with float16_t and HF literals, :823-827), else float32.  Pass
-    np.float64 for the high-precision oracle.
+    np.float64 for the high-precision oracle.  ``workers`` > 1 splits the rows over
+    threads (identical results; used by the timed CPU baseline).
     """
     if dtype is None:
         dtype = np.float16 if precision == 2 else np.float32
@@ -222,42 +259,26 @@ def sharpen(pre: np.ndarray, plan: FramePlan, sharpen_const: float = 0.2,
     up_w, up_h, ps = plan.up_w, plan.up_h, plan.pre_plane_stride
     flat = _flat_with_pad(pre, plan).astype(dtype)
     # tex = up2 * in ; len = |tex| clamped to [0,1]     (:893-907)
-    t_all = np.abs(dt(plan.up2) * flat)
+    t_all = np.abs(dt(_literal(plan.up2)) * flat)
     t_all = np.minimum(t_all, dt(1.0))
     t_all = np.maximum(t_all, dt(0.0))
-    s = dt(np.float32(sharpen_const))  # "%f" of a float -> literal of that value
+    s = dt(_literal(sharpen_const))
     out = np.empty((pre.shape[0], up_h, up_w), dtype=dtype)
-    rows_m = np.concatenate(([0], np.arange(up_h - 1)))  # max(y-1, 0)
+    nw = int(workers) if workers else 1
+    jobs = []
     for ch in range(pre.shape[0]):
-        base = ch * ps
-        n_ext = (up_h + 1) * up_w
-        e0 = t_all[base: base + n_ext].reshape(up_h + 1, up_w)            # X = x
-        ep = t_all[base + 1: base + 1 + n_ext].reshape(up_h + 1, up_w)    # X = x+1 (flat)
-        em = e0.copy()
-        em[:, 1:] = e0[:, :-1]                                              # X = max(x-1,0)
-
-        def tap(g, dy):
-            if dy == 0:
-                return g[:up_h]
-            if dy > 0:
-                return g[1:up_h + 1]
-            return g[rows_m]
-
-        l0, l1, l2 = tap(em, -1), tap(e0, -1), tap(ep, -1)
-        l3, l4, l5 = tap(em, 0), tap(e0, 0), tap(ep, 0)
-        l6, l7, l8 = tap(em, 1), tap(e0, 1), tap(ep, 1)
-        mn0 = np.minimum(l1, np.minimum(l3, np.minimum(l4, np.minimum(l5, l7))))
-        mn1 = np.minimum(mn0, np.minimum(l0, np.minimum(l2, np.minimum(l6, l8))))
-        mx0 = np.maximum(l1, np.maximum(l3, np.maximum(l4, np.maximum(l5, l7))))
-        mx1 = np.maximum(mx0, np.maximum(l0, np.maximum(l2, np.maximum(l6, l8))))
-        with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
-            minlen = dt(0.5) * (mn0 + mn1)
-            maxlen = dt(0.5) * (mx0 + mx1)
-            minlen = minlen / (dt(1.0) - minlen)
-            maxlen = (dt(1.0) - maxlen) / maxlen
-            scale = np.where(minlen < maxlen, minlen, maxlen)
-            scale = -s * np.sqrt(scale)
-            out[ch] = (l4 + scale * (((l1 + l3) + l5) + l7)) / (dt(1.0) + scale * dt(4.0))
+        if nw <= 1:
+            jobs.append((ch, 0, up_h))
+        else:
+            step = max(16, -(-up_h // nw))
+            jobs += [(ch, y0, min(y0 + step, up_h)) for y0 in range(0, up_h, step)]
+    if nw <= 1:
+        for ch, y0, y1 in jobs:
+            _sharpen_rows(t_all, ch * ps, up_w, up_h, y0, y1, s, dt, out[ch])
+    else:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(nw) as ex:
+            list(ex.map(lambda j: _sharpen_rows(t_all, j[0] * ps, up_w, up_h, j[1], j[2], s, dt, out[j[0]]), jobs))
     return out
 
 
@@ -291,7 +312,7 @@ def upscale_frame(x: np.ndarray, upscale: float = 2.0, sharpen_const: float = 0.
         sh_dtype = np.float64
     else:
         sh_dtype = None
-    out = sharpen(pre, plan, sharpen_const, precision, dtype=sh_dtype)
+    out = sharpen(pre, plan, sharpen_const, precision, dtype=sh_dtype, workers=workers)
     if precision == 2 and dtype != np.float64:
         out = out.astype(np.float16)
     elif dtype != np.float64:
