@@ -61,9 +61,9 @@ static void k_fft_test(const float2* in, float2* out, const float2* tw, const P 
     plan.template for_stages<0, 0>([&](auto st, int) {
         using St = decltype(st);
         float2 v[St::NB][St::R];
-        stage_load_compute<DIR>(st, sm, tw, T, tid, 1, 0, v);
+        stage_load_compute<DIR, 1>(st, sm, tw, T, tid, 0, v);
         B2R_SYNC();
-        stage_store(st, sm, T, tid, 1, 0, v);
+        stage_store<1>(st, sm, T, tid, 0, v);
         B2R_SYNC();
     });
     for (int i = tid; i < plan.n(); i += T) out[i] = sm[smem_pad(i)];
@@ -108,8 +108,14 @@ template <class P, int PPB> static void emu_c2r(FrameCtx& c, const P plan, const
     const float2* tw = hf.twiddles.data();
     const float scale = 1.0f / (float)c.g.up_w;
     b2r_emu::launch(grid, block, PPB * smem_padded_len(c.g.up_w) * sizeof(float2), [&] {
-        if (c.precision == 2) k_c2r_rows<P, __half, PPB>(c.spec2.data(), (__half*)c.pre.data(), tw, plan, c.dm, pairs, scale);
-        else k_c2r_rows<P, float, PPB>(c.spec2.data(), (float*)c.pre.data(), tw, plan, c.dm, pairs, scale);
+        const bool up2 = P::kStatic && (c.g.up_w == 2 * c.g.w);
+        if (c.precision == 2) {
+            if (up2) k_c2r_rows<P, __half, PPB, true>(c.spec2.data(), (__half*)c.pre.data(), tw, plan, c.dm, pairs, scale);
+            else k_c2r_rows<P, __half, PPB, false>(c.spec2.data(), (__half*)c.pre.data(), tw, plan, c.dm, pairs, scale);
+        } else {
+            if (up2) k_c2r_rows<P, float, PPB, true>(c.spec2.data(), (float*)c.pre.data(), tw, plan, c.dm, pairs, scale);
+            else k_c2r_rows<P, float, PPB, false>(c.spec2.data(), (float*)c.pre.data(), tw, plan, c.dm, pairs, scale);
+        }
     });
 }
 template <class PF, class PI, int CC>
@@ -119,6 +125,27 @@ static void emu_cols(FrameCtx& c, const PF pf, const PI pi, const HostFft& hf, c
     const float scale = 1.0f / (float)c.g.up_h;
     b2r_emu::launch(grid, block, smem_padded_len(c.g.up_h * CC) * sizeof(float2), [&] {
         k_cols<PF, PI, CC>(c.spec1.data(), c.spec2.data(), twf, twi, pf, pi, c.dm, scale);
+    });
+}
+
+// K8 exactly as launch_sharpen_kernel chooses it (b2r_sharpen.cu)
+static void emu_sharpen(const FrameDims dm, int precision, const void* pre, void* out) {
+    Dim3 grid, block;
+    const int bx = sharpen_rows_block(dm.up_w);
+    if (bx > 0) {
+        constexpr int RY = kSharpenRowsPerThread;
+        block.x = bx; grid.x = dm.up_w / 4 / bx; grid.y = (dm.up_h + RY - 1) / RY; grid.z = 3;
+        b2r_emu::launch(grid, block, 0, [&] {
+            if (precision == 2) k_sharpen_rows<__half, RY>((const __half*)pre, (__half*)out, dm);
+            else k_sharpen_rows<float, RY>((const float*)pre, (float*)out, dm);
+        });
+        return;
+    }
+    constexpr int PX = 4;
+    block.x = 64; grid.x = (dm.up_w + PX * 64 - 1) / (PX * 64); grid.y = dm.up_h; grid.z = 3;
+    b2r_emu::launch(grid, block, 0, [&] {
+        if (precision == 2) k_sharpen<__half, PX>((const __half*)pre, (__half*)out, dm);
+        else k_sharpen<float, PX>((const float*)pre, (float*)out, dm);
     });
 }
 
@@ -227,13 +254,7 @@ int b2r_emu_frame(int w, int h, float upscale, int precision, float sharpen_cons
         }
     }
     {   // K8
-        constexpr int PX = 4;
-        Dim3 grid, block; block.x = 64; grid.x = (g.up_w + PX * 64 - 1) / (PX * 64); grid.y = g.up_h; grid.z = 3;
-        const FrameDims dm = c.dm;
-        b2r_emu::launch(grid, block, 0, [&] {
-            if (precision == 2) k_sharpen<__half, PX>((const __half*)c.pre.data(), (__half*)out, dm);
-            else k_sharpen<float, PX>((const float*)c.pre.data(), (float*)out, dm);
-        });
+        emu_sharpen(c.dm, precision, c.pre.data(), out);
     }
     if (used_static) *used_static = used;
     if (spec1_dump) memcpy(spec1_dump, c.spec1.data(), c.spec1.size() * sizeof(float2));
@@ -249,12 +270,7 @@ int b2r_emu_sharpen(int w, int h, float upscale, int precision, float sharpen_co
     if (!make_geometry(w, h, upscale, precision, sharpen_const, &g, &err)) return -1;
     g.up2 = up2_lit;
     const FrameDims dm = dims_of(g);
-    constexpr int PX = 4;
-    b2r_emu::Dim3 grid, block; block.x = 64; grid.x = (g.up_w + PX * 64 - 1) / (PX * 64); grid.y = g.up_h; grid.z = 3;
-    b2r_emu::launch(grid, block, 0, [&] {
-        if (precision == 2) k_sharpen<__half, PX>((const __half*)pre, (__half*)out, dm);
-        else k_sharpen<float, PX>((const float*)pre, (float*)out, dm);
-    });
+    emu_sharpen(dm, precision, pre, out);
     return 0;
 }
 

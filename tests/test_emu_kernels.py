@@ -115,10 +115,12 @@ def test_dc_quirk_is_exercised():
     assert np.abs(r["pre"] - with_quirk).max() * plan.up2 <= 1e-5
 
 
-def test_sharpen_border_rules():
+@pytest.mark.parametrize("w,h", [(32, 16), (64, 32), (128, 12), (70, 32)])
+def test_sharpen_border_rules(w, h):
     """right neighbour of the last column = first pixel of the next row; row below the last row =
-    zero pad; (upW-1, upH-1) with upW == 2*upH reads the next channel's (0,0)."""
-    w, h = 32, 16  # upW = 64 = 2*upH
+    zero pad; (upW-1, upH-1) with upW == 2*upH reads the next channel's (0,0).  (32,16) and
+    (70,32) run the any-width kernel, (64,32) and (128,12) the vectorised rolling-window kernel
+    (upW a multiple of 128; 24 rows = three strips of 8)."""
     plan = vo.make_plan(w, h, 2.0)
     rng = np.random.default_rng(5)
     pre = np.zeros(3 * plan.pre_plane_stride + plan.up_w + 8, np.float32)

@@ -24,17 +24,17 @@ cudaError_t run_r2c(cudaStream_t s, const R2cArgs& a, int threads, size_t smem) 
 }
 cudaError_t prep_c2r(size_t smem) {
     if (smem <= 48 * 1024) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(k_c2r_rows<DynFft, float, kDynPPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_c2r_rows<DynFft, float, kDynPPB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_c2r_rows<DynFft, __half, kDynPPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    return cudaFuncSetAttribute(k_c2r_rows<DynFft, __half, kDynPPB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 cudaError_t run_c2r(cudaStream_t s, const C2rArgs& a, int threads, size_t smem) {
     const int pairs = 3 * a.dm.up_h / 2;
     dim3 block(threads, kDynPPB), grid(pairs);
     if (a.precision == 2)
-        k_c2r_rows<DynFft, __half, kDynPPB><<<grid, block, smem, s>>>(a.spec, (__half*)a.pre, a.tw, DynFft{a.dfd}, a.dm, pairs, a.scale);
+        k_c2r_rows<DynFft, __half, kDynPPB, false><<<grid, block, smem, s>>>(a.spec, (__half*)a.pre, a.tw, DynFft{a.dfd}, a.dm, pairs, a.scale);
     else
-        k_c2r_rows<DynFft, float, kDynPPB><<<grid, block, smem, s>>>(a.spec, (float*)a.pre, a.tw, DynFft{a.dfd}, a.dm, pairs, a.scale);
+        k_c2r_rows<DynFft, float, kDynPPB, false><<<grid, block, smem, s>>>(a.spec, (float*)a.pre, a.tw, DynFft{a.dfd}, a.dm, pairs, a.scale);
     return cudaGetLastError();
 }
 template <int CC> cudaError_t prep_cols(size_t smem) {

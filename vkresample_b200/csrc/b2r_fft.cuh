@@ -263,6 +263,14 @@ template <int N_, int R_, int S_, int TWOFF_, int T_> struct StaticStage {
     B2R_DEV constexpr int stride() const { return S_; }
     B2R_DEV constexpr int tw_off() const { return TWOFF_; }
     B2R_DEV void split(int j, int& q, int& p) const { q = j / S_; p = j - q * S_; }
+    // Padded-address shortcuts (smem_pad(i) = i + i/16): when the element stride between the R
+    // operands of a butterfly is a multiple of 16 (or small enough never to carry into the next
+    // group of 16) the R addresses are pad(first) + compile-time offsets -> LDS/STS immediates.
+    template <int CS> static constexpr bool read_const() { return (kNb * CS) % 16 == 0; }
+    template <int CS> static constexpr bool write_const() {
+        return (S_ * CS) % 16 == 0 ||
+               (S_ == 1 && 16 % CS == 0 && ((R_ * CS) % 16 == 0 || 16 % (R_ * CS) == 0));
+    }
 };
 template <int R_, int NB_> struct DynStage {
     static constexpr int R = R_;
@@ -275,6 +283,8 @@ template <int R_, int NB_> struct DynStage {
         q = (sd->stride > 1) ? (int)fd_div((unsigned)j, sd->divS) : j;
         p = j - q * sd->stride;
     }
+    template <int CS> static constexpr bool read_const() { return false; }
+    template <int CS> static constexpr bool write_const() { return false; }
 };
 
 // ---- stage engine --------------------------------------------------------------------------------
@@ -282,16 +292,23 @@ template <int R_, int NB_> struct DynStage {
 // cs = columns per CTA for the column kernel, so that the batch index is the fastest dimension).
 
 // shared -> registers, outer twiddle w = exp(DIR*2*pi*i*p/(S*R)) (one table load), butterfly
-template <int DIR, class St>
+template <int DIR, int CS, class St>
 B2R_DEV void stage_load_compute(const St st, const float2* sm, const float2* __restrict__ tw, int T, int tid,
-                                int cs, int c, float2 (&v)[St::NB][St::R]) {
+                                int c, float2 (&v)[St::NB][St::R]) {
     constexpr int R = St::R;
 #pragma unroll
     for (int b = 0; b < St::NB; ++b) {
         int j = tid + b * T;
         if (j < st.nb()) {
+            if constexpr (St::template read_const<CS>()) {
+                const float2* base = sm + smem_pad(j * CS + c);
+                const int step = st.nb() * CS + ((st.nb() * CS) >> 4);
 #pragma unroll
-            for (int i = 0; i < R; ++i) v[b][i] = sm[smem_pad((j + i * st.nb()) * cs + c)];
+                for (int i = 0; i < R; ++i) v[b][i] = base[i * step];
+            } else {
+#pragma unroll
+                for (int i = 0; i < R; ++i) v[b][i] = sm[smem_pad((j + i * st.nb()) * CS + c)];
+            }
             if (st.stride() > 1) {
                 int q, p;
                 st.split(j, q, p);
@@ -315,8 +332,8 @@ B2R_DEV void stage_compute_first(const St st, int T, int tid, float2 (&v)[St::NB
 }
 
 // registers -> shared at the Stockham output index  p + (j div S)*S*R + k*S
-template <class St>
-B2R_DEV void stage_store(const St st, float2* sm, int T, int tid, int cs, int c, float2 (&v)[St::NB][St::R]) {
+template <int CS, class St>
+B2R_DEV void stage_store(const St st, float2* sm, int T, int tid, int c, float2 (&v)[St::NB][St::R]) {
     constexpr int R = St::R;
 #pragma unroll
     for (int b = 0; b < St::NB; ++b) {
@@ -325,10 +342,19 @@ B2R_DEV void stage_store(const St st, float2* sm, int T, int tid, int cs, int c,
             int q, p;
             st.split(j, q, p);
             int base = q * st.stride() * R + p;
-            static_for<0, R>([&](auto k) {
-                constexpr int K = decltype(k)::value;
-                sm[smem_pad((base + K * st.stride()) * cs + c)] = v[b][dft_slot<R>(K)];
-            });
+            if constexpr (St::template write_const<CS>()) {
+                float2* dst = sm + smem_pad(base * CS + c);
+                static_for<0, R>([&](auto k) {
+                    constexpr int K = decltype(k)::value;
+                    const int off = K * st.stride() * CS;
+                    dst[off + (off >> 4)] = v[b][dft_slot<R>(K)];
+                });
+            } else {
+                static_for<0, R>([&](auto k) {
+                    constexpr int K = decltype(k)::value;
+                    sm[smem_pad((base + K * st.stride()) * CS + c)] = v[b][dft_slot<R>(K)];
+                });
+            }
         }
     }
 }

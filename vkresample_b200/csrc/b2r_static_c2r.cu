@@ -6,17 +6,24 @@ namespace b2r {
 namespace {
 template <class P, int PPB> cudaError_t prep(size_t smem) {
     if (smem <= 48 * 1024) return cudaSuccess;
-    cudaError_t e = cudaFuncSetAttribute(k_c2r_rows<P, float, PPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(k_c2r_rows<P, __half, PPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e;
+    const int n = (int)smem;
+    if ((e = cudaFuncSetAttribute(k_c2r_rows<P, float, PPB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, n))) return e;
+    if ((e = cudaFuncSetAttribute(k_c2r_rows<P, float, PPB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, n))) return e;
+    if ((e = cudaFuncSetAttribute(k_c2r_rows<P, __half, PPB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, n))) return e;
+    return cudaFuncSetAttribute(k_c2r_rows<P, __half, PPB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, n);
 }
 template <class P, int PPB> cudaError_t run(cudaStream_t s, const C2rArgs& a, int, size_t smem) {
     const int pairs = 3 * a.dm.up_h / 2;
     dim3 block(P::kT, PPB), grid((pairs + PPB - 1) / PPB);
-    if (a.precision == 2)
-        k_c2r_rows<P, __half, PPB><<<grid, block, smem, s>>>(a.spec, (__half*)a.pre, a.tw, P{}, a.dm, pairs, a.scale);
-    else
-        k_c2r_rows<P, float, PPB><<<grid, block, smem, s>>>(a.spec, (float*)a.pre, a.tw, P{}, a.dm, pairs, a.scale);
+    const bool up2 = (a.dm.up_w == 2 * a.dm.w);   // exact 2x: first-stage operand pattern is static
+    if (a.precision == 2) {
+        if (up2) k_c2r_rows<P, __half, PPB, true><<<grid, block, smem, s>>>(a.spec, (__half*)a.pre, a.tw, P{}, a.dm, pairs, a.scale);
+        else k_c2r_rows<P, __half, PPB, false><<<grid, block, smem, s>>>(a.spec, (__half*)a.pre, a.tw, P{}, a.dm, pairs, a.scale);
+    } else {
+        if (up2) k_c2r_rows<P, float, PPB, true><<<grid, block, smem, s>>>(a.spec, (float*)a.pre, a.tw, P{}, a.dm, pairs, a.scale);
+        else k_c2r_rows<P, float, PPB, false><<<grid, block, smem, s>>>(a.spec, (float*)a.pre, a.tw, P{}, a.dm, pairs, a.scale);
+    }
     return cudaGetLastError();
 }
 template <class P, int PPB> void fill(RowImpl* o, const char* name) {
