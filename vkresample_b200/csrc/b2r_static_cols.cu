@@ -3,6 +3,8 @@
 #include "b2r_launch.h"
 #include "b2r_static_sizes.h"
 
+#include <cstdlib>
+
 namespace b2r {
 namespace {
 template <class PF, class PI, int CC> cudaError_t prep(size_t smem) {
@@ -30,6 +32,13 @@ template <class PF, class PI, int CC> void fill(ColImpl* o, const char* name) {
 }  // namespace
 
 bool find_static_cols(int h, int up_h, ColImpl* out) {
+    // tuning aid: B2R_COLS_CC=2|4|8 picks another column-tile width where it is instantiated
+    const char* e = getenv("B2R_COLS_CC");
+    const int want = e ? atoi(e) : 0;
+#define X(H, UPH, CC, PF, PI) \
+    if (h == H && up_h == UPH && want == CC) { fill<PF, PI, CC>(out, "cols<" #H "->" #UPH "," #CC ">"); return true; }
+    B2R_STATIC_COLS_TUNING(X)
+#undef X
 #define X(H, UPH, CC, PF, PI) \
     if (h == H && up_h == UPH) { fill<PF, PI, CC>(out, "cols<" #H "->" #UPH ">"); return true; }
     B2R_STATIC_COLS(X)

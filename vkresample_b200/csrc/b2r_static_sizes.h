@@ -40,3 +40,8 @@ using ColI4320 = StaticFft<4320, 360, 16, 15, 6, 3>;
     X(1024, 2048, 4, ColF1024, ColI2048)       \
     X(1080, 2160, 4, ColF1080, ColI2160)       \
     X(2160, 4320, 2, ColF2160, ColI4320)
+
+// extra tile widths of the c2 column kernel, selectable with B2R_COLS_CC for tuning runs
+#define B2R_STATIC_COLS_TUNING(X)              \
+    X(1024, 2048, 2, ColF1024, ColI2048)       \
+    X(1024, 2048, 8, ColF1024, ColI2048)
