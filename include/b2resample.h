@@ -112,6 +112,17 @@ int b2r_sharpen_host(b2r_plan* plan, const void* host_pre, void* host_out);
  * layout), asynchronously on the plan's stream.  The launchResample file loop (VkResample.cpp:1627)
  * with the transfers hoisted out; used for device-resident frame streams. */
 int b2r_enqueue_device(b2r_plan* plan, const void* device_in, void* device_out);
+/* Same with HOST buffers: H2D copy + frame + D2H copy of one frame, asynchronously; host_out is valid
+ * after b2r_synchronize().  Pinned host memory is needed for the copies to overlap. */
+int b2r_enqueue_host(b2r_plan* plan, const void* host_in, void* host_out);
+/* Number of lanes (1..8, default 1) that b2r_enqueue_device / b2r_enqueue_host rotate over.  Each
+ * lane owns a stream and a private set of working buffers, so consecutive frames of a stream overlap
+ * on the GPU (and copies overlap kernels) -- the equivalent of running the reference with
+ * -numthreads N, N private VkFFT applications on one device (VkResample.cpp:1959-1969).  Frames that
+ * are in flight together must use distinct caller buffers.  b2r_execute / b2r_upload / b2r_download
+ * always use lane 0. */
+int b2r_plan_set_lanes(b2r_plan* plan, uint32_t lanes);
+uint32_t b2r_plan_lanes(const b2r_plan* plan);
 /* CUDA-event stopwatch on the plan's stream (what performVulkanUpscale's submit..fence clock is
  * to the reference, VkResample.cpp:1270-1274): start records, stop records + waits + returns ms. */
 int b2r_timer_start(b2r_plan* plan);

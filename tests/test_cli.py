@@ -59,7 +59,7 @@ def test_cli_single_image_matches_oracle(tmp_path):
     from PIL import Image
     rng = np.random.default_rng(11)
     yy, xx = np.mgrid[0:120, 0:160]
-    base = 127 + 100 * np.sin(xx / 9.0)[..., None] * np.cos(yy / 7.0 + np.arange(3))[..., None, :].reshape(120, 1, 3)
+    base = 127 + 100 * np.sin(xx / 9.0)[..., None] * np.cos(yy[..., None] / 7.0 + np.arange(3))
     img = np.clip(base + rng.integers(-20, 20, (120, 160, 3)), 0, 255).astype(np.uint8)
     src, dst = str(tmp_path / "in.png"), str(tmp_path / "out.png")
     Image.fromarray(img, "RGB").save(src)

@@ -201,3 +201,33 @@ def test_two_plans_two_threads():
     [t.start() for t in th]
     [t.join() for t in th]
     assert np.array_equal(res[0], ref) and np.array_equal(res[1], ref)
+
+
+def test_lanes_stream_matches_sequential():
+    """b2r_plan_set_lanes + b2r_enqueue_host / b2r_enqueue_device: frames in flight on several lanes
+    give bit-identical results to the one-at-a-time call sequence, in any lane"""
+    import torch
+    w, h = 512, 256
+    frames = [vo.synthetic_frame("noise", w, h, seed) for seed in range(7)]
+    with vb.Plan(w, h) as p:
+        seq = [p.upscale(f).copy() for f in frames]
+        p.set_lanes(3)
+        assert p.lanes == 3
+        h_in = [torch.from_numpy(p.pack_input(f)).pin_memory() for f in frames]
+        h_out = [torch.empty((3, p.up_h, p.up_w), dtype=torch.float32).pin_memory() for _ in frames]
+        for a, b in zip(h_in, h_out):
+            p.enqueue_host(a.data_ptr(), b.data_ptr())
+        p.synchronize()
+        for s_, b in zip(seq, h_out):
+            assert np.array_equal(s_, b.numpy())
+        # device-resident form
+        d_in = [t_.cuda() for t_ in h_in]
+        d_out = [torch.empty((3, p.up_h, p.up_w), dtype=torch.float32, device="cuda") for _ in frames]
+        torch.cuda.synchronize()
+        p.timer_start()
+        for a, b in zip(d_in, d_out):
+            p.enqueue_device(a.data_ptr(), b.data_ptr())
+        ms = p.timer_stop()
+        assert ms > 0
+        for s_, b in zip(seq, d_out):
+            assert np.array_equal(s_, b.cpu().numpy())

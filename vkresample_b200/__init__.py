@@ -31,7 +31,7 @@ EXPORTS = [
     "b2r_upscale_host", "b2r_device_input", "b2r_device_output", "b2r_download_pre_sharpen",
     "b2r_plan_pre_sharpen_bytes", "b2r_sharpen_host", "b2r_synchronize", "b2r_plan_stream",
     "b2r_plan_launch_count", "b2r_last_error", "b2r_version", "b2r_enqueue_device", "b2r_timer_start",
-    "b2r_timer_stop", "b2r_profile_kernels",
+    "b2r_timer_stop", "b2r_profile_kernels", "b2r_enqueue_host", "b2r_plan_set_lanes", "b2r_plan_lanes",
 ]
 
 
@@ -90,6 +90,10 @@ def load_library():
     L.b2r_sharpen_host.argtypes = [vp, vp, vp]
     L.b2r_synchronize.argtypes = [vp]
     L.b2r_enqueue_device.argtypes = [vp, vp, vp]
+    L.b2r_enqueue_host.argtypes = [vp, vp, vp]
+    L.b2r_plan_set_lanes.argtypes = [vp, u32]
+    L.b2r_plan_lanes.argtypes = [vp]
+    L.b2r_plan_lanes.restype = u32
     L.b2r_timer_start.argtypes = [vp]
     L.b2r_timer_stop.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     L.b2r_profile_kernels.argtypes = [vp, u32, ctypes.POINTER(ctypes.c_double)]
@@ -230,6 +234,17 @@ class Plan:
     def enqueue_device(self, device_in: int, device_out: int):
         """asynchronously process one device-resident frame (raw CUDA device pointers)"""
         _check(self._lib.b2r_enqueue_device(self._h, int(device_in), int(device_out)))
+
+    def enqueue_host(self, host_in, host_out):
+        """asynchronously upload + process + download one frame (pinned host buffers)"""
+        _check(self._lib.b2r_enqueue_host(self._h, _ptr(host_in), _ptr(host_out)))
+
+    def set_lanes(self, lanes: int):
+        _check(self._lib.b2r_plan_set_lanes(self._h, lanes))
+
+    @property
+    def lanes(self) -> int:
+        return int(self._lib.b2r_plan_lanes(self._h))
 
     def timer_start(self):
         _check(self._lib.b2r_timer_start(self._h))

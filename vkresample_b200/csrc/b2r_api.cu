@@ -54,6 +54,20 @@ int env_int(const char* name, int dflt) {
 }
 }  // namespace
 
+// One set of per-frame working buffers + a stream.  Lane 0 is the plan's primary set; extra lanes
+// (b2r_plan_set_lanes) let independent frames of a stream overlap on the GPU and let the PCIe copies
+// of one frame overlap the kernels of another -- what running the reference with -numthreads N does
+// with N private VkFFT applications on one device (VkResample.cpp:1959-1969).
+struct Lane {
+    cudaStream_t stream = nullptr;
+    void* d_in = nullptr;
+    void* d_pre = nullptr;
+    void* d_out = nullptr;
+    float2* d_spec1 = nullptr;
+    float2* d_spec2 = nullptr;
+    cudaEvent_t done = nullptr;
+};
+
 struct b2r_plan {
     int device = 0;
     uint32_t flags = 0;
@@ -77,12 +91,19 @@ struct b2r_plan {
     cudaGraphExec_t graph_exec = nullptr;
     uint64_t launches = 0;
     int kernels_per_frame = 4;
+    std::vector<Lane> extra;   // lanes 1..n-1
+    uint32_t next_lane = 0;
+    Lane lane(uint32_t i) const {
+        if (i == 0) { Lane l; l.stream = stream; l.d_in = d_in; l.d_pre = d_pre; l.d_out = d_out; l.d_spec1 = d_spec1; l.d_spec2 = d_spec2; l.done = ev1; return l; }
+        return extra[i - 1];
+    }
+    uint32_t num_lanes() const { return 1 + (uint32_t)extra.size(); }
 };
 
 namespace {
 
-int launch_sharpen(b2r_plan* p, cudaStream_t s, void* d_out = nullptr) {
-    SharpenArgs a{p->d_pre, d_out ? d_out : p->d_out, p->dm, p->g.precision};
+int launch_sharpen(b2r_plan* p, cudaStream_t s, void* d_out = nullptr, const Lane* ln = nullptr) {
+    SharpenArgs a{ln ? ln->d_pre : p->d_pre, d_out ? d_out : (ln ? ln->d_out : p->d_out), p->dm, p->g.precision};
     CU(launch_sharpen_kernel(s, a));
     return B2R_SUCCESS;
 }
@@ -90,19 +111,22 @@ int launch_sharpen(b2r_plan* p, cudaStream_t s, void* d_out = nullptr) {
 // The per-frame sequence: K1 -> fused columns -> K7 -> K8 (performVulkanUpscale body, :1260-1269)
 // ev (optional, 5 events): recorded before K1 and after each kernel for per-kernel timing.
 int launch_frame(b2r_plan* p, cudaStream_t s, const void* d_in = nullptr, void* d_out = nullptr,
-                 cudaEvent_t* ev = nullptr) {
+                 cudaEvent_t* ev = nullptr, const Lane* ln = nullptr) {
     const Geometry& g = p->g;
+    float2* spec1 = ln ? ln->d_spec1 : p->d_spec1;
+    float2* spec2 = ln ? ln->d_spec2 : p->d_spec2;
+    void* pre = ln ? ln->d_pre : p->d_pre;
     if (ev) CU(cudaEventRecord(ev[0], s));
-    R2cArgs a1{d_in ? d_in : p->d_in, p->d_spec1, p->tw_w, p->d_fd + 0, p->dm, g.precision};
+    R2cArgs a1{d_in ? d_in : (ln ? ln->d_in : p->d_in), spec1, p->tw_w, p->d_fd + 0, p->dm, g.precision};
     CU(p->k_r2c.r2c(s, a1, p->k_r2c.sched.threads, p->k_r2c.smem));
     if (ev) CU(cudaEventRecord(ev[1], s));
-    ColsArgs a2{p->d_spec1, p->d_spec2, p->tw_h, p->tw_uh, p->d_fd + 1, p->d_fd + 2, p->dm, 1.0f / (float)g.up_h};
+    ColsArgs a2{spec1, spec2, p->tw_h, p->tw_uh, p->d_fd + 1, p->d_fd + 2, p->dm, 1.0f / (float)g.up_h};
     CU(p->k_cols.launch(s, a2, p->k_cols.inv.threads, p->k_cols.smem));
     if (ev) CU(cudaEventRecord(ev[2], s));
-    C2rArgs a3{p->d_spec2, p->d_pre, p->tw_uw, p->d_fd + 3, p->dm, g.precision, 1.0f / (float)g.up_w};
+    C2rArgs a3{spec2, pre, p->tw_uw, p->d_fd + 3, p->dm, g.precision, 1.0f / (float)g.up_w};
     CU(p->k_c2r.c2r(s, a3, p->k_c2r.sched.threads, p->k_c2r.smem));
     if (ev) CU(cudaEventRecord(ev[3], s));
-    int rc = launch_sharpen(p, s, d_out);
+    int rc = launch_sharpen(p, s, d_out, ln);
     if (rc) return rc;
     if (ev) CU(cudaEventRecord(ev[4], s));
     return B2R_SUCCESS;
@@ -290,6 +314,12 @@ void b2r_plan_destroy(b2r_plan* p) {
     if (!p) return;
     cudaSetDevice(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
+    for (Lane& l : p->extra) {
+        if (l.stream) { cudaStreamSynchronize(l.stream); cudaStreamDestroy(l.stream); }
+        if (l.done) cudaEventDestroy(l.done);
+        cudaFree(l.d_in); cudaFree(l.d_pre); cudaFree(l.d_out); cudaFree(l.d_spec1); cudaFree(l.d_spec2);
+    }
+    p->extra.clear();
     if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
     if (p->graph) cudaGraphDestroy(p->graph);
     if (p->ev0) cudaEventDestroy(p->ev0);
@@ -404,12 +434,56 @@ int b2r_sharpen_host(b2r_plan* p, const void* host_pre, void* host_out) {
     return B2R_SUCCESS;
 }
 
+int b2r_plan_set_lanes(b2r_plan* p, uint32_t lanes) {
+    if (!p || lanes < 1 || lanes > 8) return fail(B2R_ERR_INVALID_ARG, "lanes must be in [1, 8]");
+    CU(cudaSetDevice(p->device));
+    CU(cudaStreamSynchronize(p->stream));
+    const Geometry& g = p->g;
+    const size_t eb = g.elem_bytes();
+    while (p->num_lanes() < lanes) {
+        Lane l;
+        CU(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
+        CU(cudaMalloc(&l.d_in, g.input_bytes()));
+        CU(cudaMalloc(&l.d_pre, g.pre_elems * eb));
+        CU(cudaMalloc(&l.d_out, g.output_bytes()));
+        CU(cudaMalloc((void**)&l.d_spec1, g.spec_in_elems() * sizeof(float2)));
+        CU(cudaMalloc((void**)&l.d_spec2, g.spec_out_elems() * sizeof(float2)));
+        CU(cudaMemset(l.d_in, 0, g.input_bytes()));
+        CU(cudaMemset(l.d_pre, 0, g.pre_elems * eb));
+        CU(cudaMemset(l.d_spec1, 0, g.spec_in_elems() * sizeof(float2)));
+        CU(cudaMemset(l.d_spec2, 0, g.spec_out_elems() * sizeof(float2)));
+        p->device_bytes += g.input_bytes() + g.pre_elems * eb + g.output_bytes() +
+                           (g.spec_in_elems() + g.spec_out_elems()) * sizeof(float2);
+        p->extra.push_back(l);
+    }
+    CU(cudaDeviceSynchronize());
+    return B2R_SUCCESS;
+}
+
+uint32_t b2r_plan_lanes(const b2r_plan* p) { return p ? p->num_lanes() : 0; }
+
 int b2r_enqueue_device(b2r_plan* p, const void* d_in, void* d_out) {
     if (!p || !d_in || !d_out) return fail(B2R_ERR_INVALID_ARG, "null argument");
     CU(cudaSetDevice(p->device));
-    int rc = launch_frame(p, p->stream, d_in, d_out);
+    const uint32_t li = p->next_lane++ % p->num_lanes();
+    const Lane l = p->lane(li);
+    int rc = launch_frame(p, l.stream, d_in, d_out, nullptr, li ? &l : nullptr);
     if (rc) return rc;
     p->launches += p->kernels_per_frame;
+    return B2R_SUCCESS;
+}
+
+int b2r_enqueue_host(b2r_plan* p, const void* host_in, void* host_out) {
+    if (!p || !host_in || !host_out) return fail(B2R_ERR_INVALID_ARG, "null argument");
+    CU(cudaSetDevice(p->device));
+    const uint32_t li = p->next_lane++ % p->num_lanes();
+    const Lane l = p->lane(li);
+    CU(cudaMemcpyAsync(l.d_in, host_in, p->g.input_bytes(), cudaMemcpyHostToDevice, l.stream));
+    int rc = launch_frame(p, l.stream, l.d_in, l.d_out, nullptr, li ? &l : nullptr);
+    if (rc) return rc;
+    p->launches += p->kernels_per_frame;
+    CU(cudaMemcpyAsync(host_out, l.d_out, p->g.output_bytes(), cudaMemcpyDeviceToHost, l.stream));
     return B2R_SUCCESS;
 }
 
@@ -417,12 +491,17 @@ int b2r_timer_start(b2r_plan* p) {
     if (!p) return fail(B2R_ERR_INVALID_ARG, "null plan");
     CU(cudaSetDevice(p->device));
     CU(cudaEventRecord(p->ev0, p->stream));
+    for (Lane& l : p->extra) CU(cudaStreamWaitEvent(l.stream, p->ev0, 0));   // every lane starts after t0
     return B2R_SUCCESS;
 }
 
 int b2r_timer_stop(b2r_plan* p, double* ms) {
     if (!p) return fail(B2R_ERR_INVALID_ARG, "null plan");
     CU(cudaSetDevice(p->device));
+    for (Lane& l : p->extra) {                                                // t1 is after every lane's tail
+        CU(cudaEventRecord(l.done, l.stream));
+        CU(cudaStreamWaitEvent(p->stream, l.done, 0));
+    }
     CU(cudaEventRecord(p->ev1, p->stream));
     CU(cudaEventSynchronize(p->ev1));
     CU(cudaGetLastError());
@@ -457,6 +536,7 @@ int b2r_profile_kernels(b2r_plan* p, uint32_t num_iter, double* ms_per_kernel) {
 int b2r_synchronize(b2r_plan* p) {
     if (!p) return fail(B2R_ERR_INVALID_ARG, "null plan");
     CU(cudaSetDevice(p->device));
+    for (Lane& l : p->extra) CU(cudaStreamSynchronize(l.stream));
     CU(cudaStreamSynchronize(p->stream));
     return B2R_SUCCESS;
 }
