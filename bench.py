@@ -253,6 +253,25 @@ def run_b200(args):
     if dist is not None:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * e_steps * e_frames / float(te.item())
+    # ---- the same through the byte-pixel extension (u8 RGB in -> u8 RGB out, conversions on the GPU)
+    u_in = [torch.from_numpy(rng.integers(0, 256, (h, w, 3), dtype=np.uint8)).pin_memory() for _ in range(n_host)]
+    u_out = [torch.empty((plan.up_h, plan.up_w, 3), dtype=torch.uint8).pin_memory() for _ in range(n_host)]
+    for i in range(n_host):
+        plan.enqueue_host_u8(u_in[i].data_ptr(), u_out[i].data_ptr())
+    plan.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for st in range(e_steps):
+        for i in range(e_frames):
+            k = (st * e_frames + i) % n_host
+            plan.enqueue_host_u8(u_in[k].data_ptr(), u_out[k].data_ptr())
+        plan.synchronize()
+    u_dt = time.perf_counter() - t0
+    tu = torch.tensor([u_dt], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tu, op=dist.ReduceOp.MAX)
+    e2e_u8_value = world * e_steps * e_frames / float(tu.item())
+
     result_checksum = float(np.frombuffer(h_out[0].numpy().tobytes()[:4096], dtype=np_dt).astype(np.float64).sum())
 
     # ---- roofline of the dominant kernel (separate pass, events between kernels, same workload)
@@ -298,6 +317,11 @@ def run_b200(args):
                         "d2h_bytes_per_step": e_frames * plan.output_bytes, "frames_per_step": e_frames,
                         "steps": e_steps, "api": "b2r_enqueue_host + b2r_synchronize (pinned host in -> pinned host out)",
                         "checksum": result_checksum},
+                "e2e_u8": {"value": e2e_u8_value, "unit": UNIT, "h2d_bytes_per_step": e_frames * 3 * w * h,
+                           "d2h_bytes_per_step": e_frames * 3 * plan.up_w * plan.up_h, "frames_per_step": e_frames,
+                           "steps": e_steps, "api": "b2r_enqueue_host_u8 (u8 RGB in -> u8 RGB out, /255 fill and truncating "
+                                                    "quantiser of launchResample run on the GPU)",
+                           "checksum": int(u_out[0].numpy()[:8, :8].astype(np.int64).sum())},
                 "gpu_launches": int(launches), "wall_s_timed_region": t_wall,
                 "roofline": roofline, "clocks": clocks}
         if cpu:

@@ -115,6 +115,17 @@ int b2r_enqueue_device(b2r_plan* plan, const void* device_in, void* device_out);
 /* Same with HOST buffers: H2D copy + frame + D2H copy of one frame, asynchronously; host_out is valid
  * after b2r_synchronize().  Pinned host memory is needed for the copies to overlap. */
 int b2r_enqueue_host(b2r_plan* plan, const void* host_in, void* host_out);
+/* Byte-pixel forms (extension; the reference README's planned "reading data in uint8"): the host
+ * loops around the hot path -- in[c][j][i] = u8[j][i][c]/255 (VkResample.cpp:1636-1685) and
+ * u8[j][i][c] = (uchar)(255.0*out[c][j][i]) (VkResample.cpp:1708-1748) -- run as two small kernels, so a
+ * frame crosses PCIe as 3*W*H + 3*upW*upH bytes instead of 4x (fp32) / 2x (fp16) that.  host buffers
+ * are interleaved RGB (stb_image's layout).  upload_u8/download_u8 pair with b2r_execute on lane 0;
+ * enqueue_host_u8 is the asynchronous per-lane form (results valid after b2r_synchronize). */
+size_t b2r_plan_input_u8_bytes(const b2r_plan* plan);
+size_t b2r_plan_output_u8_bytes(const b2r_plan* plan);
+int b2r_upload_u8(b2r_plan* plan, const unsigned char* host_rgb);
+int b2r_download_u8(b2r_plan* plan, unsigned char* host_rgb);
+int b2r_enqueue_host_u8(b2r_plan* plan, const unsigned char* host_rgb_in, unsigned char* host_rgb_out);
 /* Number of lanes (1..8, default 1) that b2r_enqueue_device / b2r_enqueue_host rotate over.  Each
  * lane owns a stream and a private set of working buffers, so consecutive frames of a stream overlap
  * on the GPU (and copies overlap kernels) -- the equivalent of running the reference with

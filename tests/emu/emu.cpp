@@ -263,6 +263,30 @@ int b2r_emu_frame(int w, int h, float upscale, int precision, float sharpen_cons
     return 0;
 }
 
+// the u8 pixel-format kernels (precision 0/2) on a w x h frame / its upscaled output
+int b2r_emu_u8_to_planar(int w, int h, int precision, const unsigned char* rgb, void* planar) {
+    Geometry g; std::string err;
+    if (!make_geometry(w, h, 1.0f, precision, 0.2f, &g, &err)) return -1;
+    const FrameDims dm = dims_of(g);
+    Dim3 grid, block; block.x = 64; grid.x = (unsigned)(((size_t)w * h / 4 + 63) / 64);
+    b2r_emu::launch(grid, block, 0, [&] {
+        if (precision == 2) k_u8_to_planar<__half>(rgb, (__half*)planar, dm);
+        else k_u8_to_planar<float>(rgb, (float*)planar, dm);
+    });
+    return 0;
+}
+int b2r_emu_planar_to_u8(int w, int h, int precision, const void* planar, unsigned char* rgb) {
+    Geometry g; std::string err;
+    if (!make_geometry(w, h, 1.0f, precision, 0.2f, &g, &err)) return -1;   // up = 1: out dims == in dims
+    const FrameDims dm = dims_of(g);
+    Dim3 grid, block; block.x = 64; grid.x = (unsigned)(((size_t)w * h / 4 + 63) / 64);
+    b2r_emu::launch(grid, block, 0, [&] {
+        if (precision == 2) k_planar_to_u8<__half>((const __half*)planar, rgb, dm);
+        else k_planar_to_u8<float>((const float*)planar, rgb, dm);
+    });
+    return 0;
+}
+
 // sharpen alone on a caller-provided padded plane buffer (bit-exactness test of K8)
 int b2r_emu_sharpen(int w, int h, float upscale, int precision, float sharpen_const, float up2_lit,
                     const void* pre, void* out) {

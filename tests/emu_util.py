@@ -27,6 +27,8 @@ def lib():
                                      ctypes.c_float, ctypes.c_int, ctypes.c_int] + [ctypes.c_void_p] * 7)
         L.b2r_emu_sharpen.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_float,
                                       ctypes.c_float, ctypes.c_void_p, ctypes.c_void_p]
+        L.b2r_emu_u8_to_planar.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+        L.b2r_emu_planar_to_u8.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         _LIB = L
     return _LIB
 

@@ -132,3 +132,34 @@ def test_sharpen_border_rules(w, h):
     assert rc == 0
     ref = vo.sharpen(eu.unpack_pre(pre, plan), plan, 0.2, 0)
     assert np.array_equal(ref.view(np.uint32), out.view(np.uint32))
+
+
+@pytest.mark.parametrize("prec", [0, 2])
+def test_u8_pixel_kernels(prec):
+    """GPU forms of the reference's host loops: u8/255 fill (VkResample.cpp:1636-1685) and the
+    truncating, wrapping quantiser (:1708-1748) -- all 256 byte values, negative / >1 / huge floats"""
+    import ctypes
+    L = eu.lib()
+    w, h = 32, 8
+    rgb = (np.arange(w * h * 3) % 256).astype(np.uint8).reshape(h, w, 3)
+    dt = np.float16 if prec == 2 else np.float32
+    planar = np.zeros(3 * (w + 2) * h, dt)
+    assert L.b2r_emu_u8_to_planar(w, h, prec, rgb.ctypes.data_as(ctypes.c_void_p), planar.ctypes.data_as(ctypes.c_void_p)) == 0
+    ref = vo.fill_input(rgb, prec)
+    got = np.stack([planar[c * (w + 2) * h: c * (w + 2) * h + w * h].reshape(h, w) for c in range(3)])
+    assert np.array_equal(got.view(np.uint16 if prec == 2 else np.uint32), ref.view(np.uint16 if prec == 2 else np.uint32))
+    # quantiser: compact planes [3][h][w] (up = 1 geometry)
+    rng = np.random.default_rng(2)
+    vals = rng.uniform(-0.02, 1.02, (3, h, w)).astype(dt)
+    vals[0, 0, :8] = np.array([0.0, 1.0, -1.0 / 255, -1.2 / 255, 256.0 / 255, 1.004, -0.0039, 100.5]).astype(dt)
+    if prec == 0:
+        vals[1, 0, :3] = [3e9, -3e9, np.nan]
+    out = np.zeros((h, w, 3), np.uint8)
+    assert L.b2r_emu_planar_to_u8(w, h, prec, vals.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p)) == 0
+    with np.errstate(invalid="ignore"):
+        q = 255.0 * vals.astype(np.float64)
+        ok = (q > -2147483648.0) & (q < 2147483648.0)
+        expect = np.where(ok, np.trunc(np.where(ok, q, 0)).astype(np.int64) & 0xFF, 0).astype(np.uint8)
+    assert np.array_equal(out, np.moveaxis(expect, 0, -1))
+    finite_small = np.moveaxis(ok & (np.abs(np.nan_to_num(q)) < 1e6), 0, -1)
+    assert np.array_equal(out[finite_small], vo.quantise(vals)[finite_small])

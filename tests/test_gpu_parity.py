@@ -231,3 +231,42 @@ def test_lanes_stream_matches_sequential():
         assert ms > 0
         for s_, b in zip(seq, d_out):
             assert np.array_equal(s_, b.cpu().numpy())
+
+
+@pytest.mark.parametrize("w,h,prec", [(256, 128, 0), (1920, 1080, 0), (640, 360, 2)])
+def test_u8_api_matches_oracle(w, h, prec):
+    """b2r_upload_u8 / b2r_download_u8: PNG pixels in -> PNG pixels out, conversions on the GPU;
+    within 1 LSB (on the u8 circle) of the oracle's launchResample restatement"""
+    rng = np.random.default_rng(w)
+    yy, xx = np.mgrid[0:h, 0:w]
+    img = np.clip(127 + 90 * np.sin(xx / 11.0)[..., None] * np.cos(yy[..., None] / 13.0 + np.arange(3))
+                  + rng.integers(-25, 25, (h, w, 3)), 0, 255).astype(np.uint8)
+    with vb.Plan(w, h, 2.0, prec, 0.2) as p:
+        got = p.upscale_u8(img)
+        # the float API on the same pixels, quantised by the oracle, must agree byte for byte
+        via_float = vo.quantise(p.upscale(vo.fill_input(img, prec)))
+        assert np.array_equal(got, via_float)
+    ref = vo.upscale_u8(img, 2.0, 0.2, prec, dtype=np.float64, workers=WORKERS)
+    d = np.abs(got.astype(np.int16) - ref.astype(np.int16))
+    d = np.minimum(d, 256 - d)
+    if prec == 0:
+        assert d.max() <= 1 and (d == 0).mean() > 0.995
+    else:
+        assert d[:-1].max() <= 3
+
+
+def test_u8_stream_lanes():
+    import torch
+    w, h = 512, 256
+    rng = np.random.default_rng(9)
+    frames = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for _ in range(5)]
+    with vb.Plan(w, h) as p:
+        seq = [p.upscale_u8(f).copy() for f in frames]
+        p.set_lanes(3)
+        h_in = [torch.from_numpy(f).pin_memory() for f in frames]
+        h_out = [torch.empty((p.up_h, p.up_w, 3), dtype=torch.uint8).pin_memory() for _ in frames]
+        for a, b in zip(h_in, h_out):
+            p.enqueue_host_u8(a.data_ptr(), b.data_ptr())
+        p.synchronize()
+        for s_, b in zip(seq, h_out):
+            assert np.array_equal(s_, b.numpy())

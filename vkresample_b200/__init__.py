@@ -32,6 +32,7 @@ EXPORTS = [
     "b2r_plan_pre_sharpen_bytes", "b2r_sharpen_host", "b2r_synchronize", "b2r_plan_stream",
     "b2r_plan_launch_count", "b2r_last_error", "b2r_version", "b2r_enqueue_device", "b2r_timer_start",
     "b2r_timer_stop", "b2r_profile_kernels", "b2r_enqueue_host", "b2r_plan_set_lanes", "b2r_plan_lanes",
+    "b2r_plan_input_u8_bytes", "b2r_plan_output_u8_bytes", "b2r_upload_u8", "b2r_download_u8", "b2r_enqueue_host_u8",
 ]
 
 
@@ -75,7 +76,8 @@ def load_library():
     L.b2r_plan_create.argtypes = [ctypes.POINTER(vp), ctypes.c_int, u32, u32, f32, u32, f32, u32]
     L.b2r_plan_destroy.argtypes = [vp]
     L.b2r_plan_destroy.restype = None
-    for name in ("b2r_plan_input_bytes", "b2r_plan_output_bytes", "b2r_plan_pre_sharpen_bytes"):
+    for name in ("b2r_plan_input_bytes", "b2r_plan_output_bytes", "b2r_plan_pre_sharpen_bytes",
+                 "b2r_plan_input_u8_bytes", "b2r_plan_output_u8_bytes"):
         getattr(L, name).argtypes = [vp]
         getattr(L, name).restype = ctypes.c_size_t
     L.b2r_plan_get_info.argtypes = [vp, ctypes.POINTER(PlanInfo)]
@@ -91,6 +93,9 @@ def load_library():
     L.b2r_synchronize.argtypes = [vp]
     L.b2r_enqueue_device.argtypes = [vp, vp, vp]
     L.b2r_enqueue_host.argtypes = [vp, vp, vp]
+    L.b2r_upload_u8.argtypes = [vp, vp]
+    L.b2r_download_u8.argtypes = [vp, vp]
+    L.b2r_enqueue_host_u8.argtypes = [vp, vp, vp]
     L.b2r_plan_set_lanes.argtypes = [vp, u32]
     L.b2r_plan_lanes.argtypes = [vp]
     L.b2r_plan_lanes.restype = u32
@@ -238,6 +243,19 @@ class Plan:
     def enqueue_host(self, host_in, host_out):
         """asynchronously upload + process + download one frame (pinned host buffers)"""
         _check(self._lib.b2r_enqueue_host(self._h, _ptr(host_in), _ptr(host_out)))
+
+    def upscale_u8(self, rgb: np.ndarray) -> np.ndarray:
+        """[H,W,3] uint8 in -> [upH,upW,3] uint8 out; both pixel conversions run on the GPU"""
+        rgb = np.ascontiguousarray(rgb, np.uint8)
+        assert rgb.shape == (self.h, self.w, 3), rgb.shape
+        out = np.empty((self.up_h, self.up_w, 3), np.uint8)
+        _check(self._lib.b2r_upload_u8(self._h, rgb.ctypes.data))
+        self.execute(1)
+        _check(self._lib.b2r_download_u8(self._h, out.ctypes.data))
+        return out
+
+    def enqueue_host_u8(self, host_in, host_out):
+        _check(self._lib.b2r_enqueue_host_u8(self._h, _ptr(host_in), _ptr(host_out)))
 
     def set_lanes(self, lanes: int):
         _check(self._lib.b2r_plan_set_lanes(self._h, lanes))

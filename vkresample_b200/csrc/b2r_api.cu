@@ -66,6 +66,8 @@ struct Lane {
     float2* d_spec1 = nullptr;
     float2* d_spec2 = nullptr;
     cudaEvent_t done = nullptr;
+    unsigned char* u8_in = nullptr;    // interleaved u8 staging, allocated on first use of the u8 API
+    unsigned char* u8_out = nullptr;
 };
 
 struct b2r_plan {
@@ -91,6 +93,8 @@ struct b2r_plan {
     cudaGraphExec_t graph_exec = nullptr;
     uint64_t launches = 0;
     int kernels_per_frame = 4;
+    unsigned char* u8_in0 = nullptr;   // lane 0's u8 staging
+    unsigned char* u8_out0 = nullptr;
     std::vector<Lane> extra;   // lanes 1..n-1
     uint32_t next_lane = 0;
     Lane lane(uint32_t i) const {
@@ -318,7 +322,9 @@ void b2r_plan_destroy(b2r_plan* p) {
         if (l.stream) { cudaStreamSynchronize(l.stream); cudaStreamDestroy(l.stream); }
         if (l.done) cudaEventDestroy(l.done);
         cudaFree(l.d_in); cudaFree(l.d_pre); cudaFree(l.d_out); cudaFree(l.d_spec1); cudaFree(l.d_spec2);
+        cudaFree(l.u8_in); cudaFree(l.u8_out);
     }
+    cudaFree(p->u8_in0); cudaFree(p->u8_out0);
     p->extra.clear();
     if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
     if (p->graph) cudaGraphDestroy(p->graph);
@@ -484,6 +490,67 @@ int b2r_enqueue_host(b2r_plan* p, const void* host_in, void* host_out) {
     if (rc) return rc;
     p->launches += p->kernels_per_frame;
     CU(cudaMemcpyAsync(host_out, l.d_out, p->g.output_bytes(), cudaMemcpyDeviceToHost, l.stream));
+    return B2R_SUCCESS;
+}
+
+size_t b2r_plan_input_u8_bytes(const b2r_plan* p) { return p ? 3ull * p->g.w * p->g.h : 0; }
+size_t b2r_plan_output_u8_bytes(const b2r_plan* p) { return p ? 3ull * p->g.up_w * p->g.up_h : 0; }
+
+namespace {
+int u8_buffers(b2r_plan* p, uint32_t li, unsigned char** in, unsigned char** out) {
+    unsigned char** pin = li ? &p->extra[li - 1].u8_in : &p->u8_in0;
+    unsigned char** pout = li ? &p->extra[li - 1].u8_out : &p->u8_out0;
+    if (!*pin) {
+        CU(cudaMalloc((void**)pin, b2r_plan_input_u8_bytes(p)));
+        CU(cudaMalloc((void**)pout, b2r_plan_output_u8_bytes(p)));
+        p->device_bytes += b2r_plan_input_u8_bytes(p) + b2r_plan_output_u8_bytes(p);
+    }
+    *in = *pin; *out = *pout;
+    return B2R_SUCCESS;
+}
+}  // namespace
+
+int b2r_upload_u8(b2r_plan* p, const unsigned char* host_hwc) {
+    if (!p || !host_hwc) return fail(B2R_ERR_INVALID_ARG, "null argument");
+    CU(cudaSetDevice(p->device));
+    unsigned char *in, *out;
+    int rc = u8_buffers(p, 0, &in, &out);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(in, host_hwc, b2r_plan_input_u8_bytes(p), cudaMemcpyHostToDevice, p->stream));
+    CU(launch_u8_to_planar(p->stream, in, p->d_in, p->dm, p->g.precision));
+    p->launches += 1;
+    CU(cudaStreamSynchronize(p->stream));
+    return B2R_SUCCESS;
+}
+
+int b2r_download_u8(b2r_plan* p, unsigned char* host_hwc) {
+    if (!p || !host_hwc) return fail(B2R_ERR_INVALID_ARG, "null argument");
+    CU(cudaSetDevice(p->device));
+    unsigned char *in, *out;
+    int rc = u8_buffers(p, 0, &in, &out);
+    if (rc) return rc;
+    CU(launch_planar_to_u8(p->stream, p->d_out, out, p->dm, p->g.precision));
+    p->launches += 1;
+    CU(cudaMemcpyAsync(host_hwc, out, b2r_plan_output_u8_bytes(p), cudaMemcpyDeviceToHost, p->stream));
+    CU(cudaStreamSynchronize(p->stream));
+    return B2R_SUCCESS;
+}
+
+int b2r_enqueue_host_u8(b2r_plan* p, const unsigned char* host_in, unsigned char* host_out) {
+    if (!p || !host_in || !host_out) return fail(B2R_ERR_INVALID_ARG, "null argument");
+    CU(cudaSetDevice(p->device));
+    const uint32_t li = p->next_lane++ % p->num_lanes();
+    const Lane l = p->lane(li);
+    unsigned char *in, *out;
+    int rc = u8_buffers(p, li, &in, &out);
+    if (rc) return rc;
+    CU(cudaMemcpyAsync(in, host_in, b2r_plan_input_u8_bytes(p), cudaMemcpyHostToDevice, l.stream));
+    CU(launch_u8_to_planar(l.stream, in, l.d_in, p->dm, p->g.precision));
+    rc = launch_frame(p, l.stream, l.d_in, l.d_out, nullptr, li ? &l : nullptr);
+    if (rc) return rc;
+    CU(launch_planar_to_u8(l.stream, l.d_out, out, p->dm, p->g.precision));
+    p->launches += p->kernels_per_frame + 2;
+    CU(cudaMemcpyAsync(host_out, out, b2r_plan_output_u8_bytes(p), cudaMemcpyDeviceToHost, l.stream));
     return B2R_SUCCESS;
 }
 

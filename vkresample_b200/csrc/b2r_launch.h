@@ -63,5 +63,7 @@ void get_dynamic_c2r(RowImpl* out);
 void get_dynamic_cols(int cc, ColImpl* out);
 
 cudaError_t launch_sharpen_kernel(cudaStream_t s, const SharpenArgs& a);
+cudaError_t launch_u8_to_planar(cudaStream_t s, const unsigned char* src, void* dst, const FrameDims& dm, int precision);
+cudaError_t launch_planar_to_u8(cudaStream_t s, const void* src, unsigned char* dst, const FrameDims& dm, int precision);
 
 }  // namespace b2r

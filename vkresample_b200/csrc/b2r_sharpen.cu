@@ -1,4 +1,4 @@
-// b2r_sharpen.cu -- K8 launcher (CAS-style sharpen, see b2r_kernels.cuh).
+// b2r_sharpen.cu -- launchers of K8 (CAS-style sharpen) and of the u8 pixel-format kernels (b2r_kernels.cuh).
 #include "b2r_launch.h"
 
 namespace b2r {
@@ -19,6 +19,20 @@ cudaError_t launch_sharpen_kernel(cudaStream_t s, const SharpenArgs& a) {
         k_sharpen<__half, PX><<<grid, block, 0, s>>>((const __half*)a.pre, (__half*)a.out, a.dm);
     else
         k_sharpen<float, PX><<<grid, block, 0, s>>>((const float*)a.pre, (float*)a.out, a.dm);
+    return cudaGetLastError();
+}
+cudaError_t launch_u8_to_planar(cudaStream_t s, const unsigned char* src, void* dst, const FrameDims& dm, int precision) {
+    const size_t n4 = ((size_t)dm.w * dm.h + 3) / 4;
+    dim3 block(256), grid((unsigned)((n4 + 255) / 256));
+    if (precision == 2) k_u8_to_planar<__half><<<grid, block, 0, s>>>(src, (__half*)dst, dm);
+    else k_u8_to_planar<float><<<grid, block, 0, s>>>(src, (float*)dst, dm);
+    return cudaGetLastError();
+}
+cudaError_t launch_planar_to_u8(cudaStream_t s, const void* src, unsigned char* dst, const FrameDims& dm, int precision) {
+    const size_t n4 = ((size_t)dm.up_w * dm.up_h + 3) / 4;
+    dim3 block(256), grid((unsigned)((n4 + 255) / 256));
+    if (precision == 2) k_planar_to_u8<__half><<<grid, block, 0, s>>>((const __half*)src, dst, dm);
+    else k_planar_to_u8<float><<<grid, block, 0, s>>>((const float*)src, dst, dm);
     return cudaGetLastError();
 }
 }  // namespace b2r

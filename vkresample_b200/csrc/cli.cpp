@@ -21,8 +21,6 @@
 #include <thread>
 #include <vector>
 
-#include <cuda_fp16.h>  // host-side binary16 conversion only (replaces half_lib/half.hpp)
-
 #include "b2resample.h"
 
 // ------------------------------------------------------------------------------------------- PNG
@@ -214,8 +212,7 @@ static int launch_resample(Config cfg) {
     b2r_plan_get_info(plan, &info);
     if (cfg.thread_id == 0)
         printf("VRAM per thread: %d MB Total: %d MB\n", (int)(info.device_bytes >> 20), (int)(cfg.num_threads * (info.device_bytes >> 20)));
-    const size_t in_plane = (size_t)(w + 2) * h, out_plane = (size_t)info.up_w * info.up_h;
-    std::vector<unsigned char> host_in(info.input_bytes, 0), host_out(info.output_bytes);
+    const size_t out_plane = (size_t)info.up_w * info.up_h;
     std::vector<unsigned char> png_out(out_plane * 3);
 
     uint32_t local_files = 1;
@@ -230,37 +227,15 @@ static int launch_resample(Config cfg) {
             if (!png::load_rgb(name, &rgb, &w2, &h2, &err)) { printf("Image not found\n"); return 5; }
             if (w2 != w || h2 != h) { printf("Image %s has a different size\n", name); return -1; }
         }
-        // u8 HWC -> planar [0,1]; the division is done in double like the reference (:1644)
-        if (cfg.precision == 2) {
-            __half* p = reinterpret_cast<__half*>(host_in.data());
-            for (int v = 0; v < 3; ++v)
-                for (int j = 0; j < h; ++j)
-                    for (int i = 0; i < w; ++i)
-                        p[i + (size_t)j * w + v * in_plane] = __float2half_rn((float)((double)rgb[v + 3 * (i + (size_t)j * w)] / 255.0));
-        } else {
-            float* p = reinterpret_cast<float*>(host_in.data());
-            for (int v = 0; v < 3; ++v)
-                for (int j = 0; j < h; ++j)
-                    for (int i = 0; i < w; ++i)
-                        p[i + (size_t)j * w + v * in_plane] = (float)((double)rgb[v + 3 * (i + (size_t)j * w)] / 255.0);
-        }
-        if ((rc = b2r_upload(plan, host_in.data()))) { printf("upload failed: %s\n", b2r_last_error()); return rc; }
+        // u8 HWC -> planar [0,1] (VkResample.cpp:1636-1685) runs on the GPU: b2r_upload_u8 ships the
+        // interleaved bytes and converts there (same values: (float)((double)u8/255.0), or RN to half)
+        if ((rc = b2r_upload_u8(plan, rgb.data()))) { printf("upload failed: %s\n", b2r_last_error()); return rc; }
         double ms = 0.0;
         if ((rc = b2r_execute(plan, cfg.num_iter, &ms))) { printf("execute failed: %s\n", b2r_last_error()); return rc; }
         if (!cfg.upload_files)
             printf("VkResample %0.1fx upscale: %dx%d to %dx%d Time: %0.3f ms\n", cfg.upscale, w, h, (int)info.up_w, (int)info.up_h, ms);
-        if ((rc = b2r_download(plan, host_out.data()))) { printf("download failed: %s\n", b2r_last_error()); return rc; }
-        // planar -> u8 HWC with the reference's truncating cast (:1715)
-        for (int v = 0; v < 3; ++v)
-            for (uint32_t j = 0; j < info.up_h; ++j)
-                for (uint32_t i = 0; i < info.up_w; ++i) {
-                    size_t src = i + (size_t)j * info.up_w + v * out_plane;
-                    double val = cfg.precision == 2 ? (double)__half2float(reinterpret_cast<__half*>(host_out.data())[src])
-                                                    : (double)reinterpret_cast<float*>(host_out.data())[src];
-                    double q = 255.0 * val;
-                    png_out[v + 3 * (i + (size_t)j * info.up_w)] =
-                        (q > -2147483648.0 && q < 2147483647.0) ? (unsigned char)(int)q : 0;
-                }
+        // planar -> u8 HWC with the reference's truncating cast (:1715), also on the GPU
+        if ((rc = b2r_download_u8(plan, png_out.data()))) { printf("download failed: %s\n", b2r_last_error()); return rc; }
         char oname[512];
         if (cfg.upload_files) snprintf(oname, sizeof oname, "%s/%06d.png", cfg.ofolder, f * cfg.num_threads + cfg.thread_id + 1);
         else if (cfg.output) snprintf(oname, sizeof oname, "%s", cfg.output);
