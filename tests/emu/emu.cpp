@@ -102,8 +102,28 @@ template <class P, int PPB> static void emu_r2c(FrameCtx& c, const P plan, const
         else k_r2c_rows<P, float, PPB>((const float*)c.in, c.spec1.data(), tw, plan, c.dm, pairs);
     });
 }
+static int g_c2r_bulk = 0;   // emulate the bulk-copy (persistent) C2R kernel instead of the direct one
+
 template <class P, int PPB> static void emu_c2r(FrameCtx& c, const P plan, const HostFft& hf) {
     int pairs = 3 * c.g.up_h / 2;
+    if (g_c2r_bulk) {
+        if constexpr (P::kStatic) {
+            Dim3 grid, block; block.x = hf.desc.threads; grid.x = 5;   // few persistent CTAs, many trips
+            const float2* tw = hf.twiddles.data();
+            const float scale = 1.0f / (float)c.g.up_w;
+            const bool up2 = (c.g.up_w == 2 * c.g.w);
+            b2r_emu::launch(grid, block, c2r_bulk_smem_bytes(P::kN, c.g.nx), [&] {
+                if (c.precision == 2) {
+                    if (up2) k_c2r_rows_bulk<P, __half, true>(c.spec2.data(), (__half*)c.pre.data(), tw, plan, c.dm, pairs, scale);
+                    else k_c2r_rows_bulk<P, __half, false>(c.spec2.data(), (__half*)c.pre.data(), tw, plan, c.dm, pairs, scale);
+                } else {
+                    if (up2) k_c2r_rows_bulk<P, float, true>(c.spec2.data(), (float*)c.pre.data(), tw, plan, c.dm, pairs, scale);
+                    else k_c2r_rows_bulk<P, float, false>(c.spec2.data(), (float*)c.pre.data(), tw, plan, c.dm, pairs, scale);
+                }
+            });
+            return;
+        }
+    }
     Dim3 grid, block; block.x = hf.desc.threads; block.y = PPB; grid.x = (pairs + PPB - 1) / PPB;
     const float2* tw = hf.twiddles.data();
     const float scale = 1.0f / (float)c.g.up_w;
@@ -150,6 +170,8 @@ static void emu_sharpen(const FrameDims dm, int precision, const void* pre, void
 }
 
 extern "C" {
+
+void b2r_emu_set_c2r_bulk(int on) { g_c2r_bulk = on; }
 
 // returns number of stages (>0) or -1; radices[] receives the schedule
 int b2r_emu_schedule(int n, int* radices, int* threads) {

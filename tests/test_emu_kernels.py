@@ -163,3 +163,20 @@ def test_u8_pixel_kernels(prec):
     assert np.array_equal(out, np.moveaxis(expect, 0, -1))
     finite_small = np.moveaxis(ok & (np.abs(np.nan_to_num(q)) < 1e6), 0, -1)
     assert np.array_equal(out[finite_small], vo.quantise(vals)[finite_small])
+
+
+@pytest.mark.parametrize("prec", [0, 2])
+def test_c2r_bulk_copy_variant(prec):
+    """persistent C2R kernel whose operands are staged in shared memory (cp.async.bulk + mbarrier on
+    the GPU; a plain copy by thread 0 in the emulator): same plane as the direct-load kernel"""
+    w, h = 256, 128
+    plan = vo.make_plan(w, h, 2.0)
+    x = vo.synthetic_frame("noise", w, h).astype(np.float16 if prec == 2 else np.float32)
+    a = eu.frame(x, 2.0, prec, 0.2, plan)
+    eu.lib().b2r_emu_set_c2r_bulk(1)
+    try:
+        b = eu.frame(x, 2.0, prec, 0.2, plan)
+    finally:
+        eu.lib().b2r_emu_set_c2r_bulk(0)
+    assert a["used_static"] == 7 and b["used_static"] == 7
+    assert np.array_equal(a["pre_flat"], b["pre_flat"]) and np.array_equal(a["out"], b["out"])

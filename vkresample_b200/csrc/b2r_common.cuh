@@ -60,4 +60,31 @@ extern thread_local Ctx g_ctx;
 #endif
 #define B2R_LAUNCH_BOUNDS(t, b) __launch_bounds__(t, b)
 extern __shared__ __align__(16) unsigned char b2r_dyn_smem[];
+
+// ---- mbarrier + bulk async copy (the copy engine behind TMA; SASS: UBLKCP / SYNCS) ----------------
+__device__ __forceinline__ unsigned b2r_smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void b2r_mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(b2r_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void b2r_mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void b2r_mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b2r_smem_u32(bar)), "r"(bytes) : "memory");
+}
+// global -> shared bulk copy; dst/src 16-byte aligned, bytes a multiple of 16; completes on `bar`
+__device__ __forceinline__ void b2r_bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     b2r_smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(b2r_smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void b2r_mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(b2r_smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!done);
+}
 #endif

@@ -2,6 +2,8 @@
 #include "b2r_launch.h"
 #include "b2r_static_sizes.h"
 
+#include <cstdlib>
+
 namespace b2r {
 namespace {
 template <class P, int PPB> cudaError_t prep(size_t smem) {
@@ -26,6 +28,39 @@ template <class P, int PPB> cudaError_t run(cudaStream_t s, const C2rArgs& a, in
     }
     return cudaGetLastError();
 }
+// ---- bulk-copy (persistent, mbarrier-prefetched) variant ------------------------------------------
+// grid = resident CTAs of the device (see DESIGN.md section 4 for the measured comparison with the
+// direct-load kernel).
+constexpr size_t kBulkSmemMax = 16 + 4 * 4100 * sizeof(float2);   // staging for nx <= 4100 (W <= 8198)
+template <class P> cudaError_t prep_bulk(size_t) {
+    const int n = (int)(kBulkSmemMax + smem_padded_len(P::kN) * sizeof(float2));
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(k_c2r_rows_bulk<P, float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, n))) return e;
+    if ((e = cudaFuncSetAttribute(k_c2r_rows_bulk<P, float, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, n))) return e;
+    if ((e = cudaFuncSetAttribute(k_c2r_rows_bulk<P, __half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, n))) return e;
+    return cudaFuncSetAttribute(k_c2r_rows_bulk<P, __half, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, n);
+}
+template <class P, class TOut, bool UP2> cudaError_t run_bulk_t(cudaStream_t s, const C2rArgs& a) {
+    const int pairs = 3 * a.dm.up_h / 2;
+    const size_t smem = c2r_bulk_smem_bytes(P::kN, a.dm.nx);
+    static thread_local int dev_cached = -1, sms = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != dev_cached) { cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); dev_cached = dev; }
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_c2r_rows_bulk<P, TOut, UP2>, P::kT, smem);
+    if (e != cudaSuccess) return e;
+    int grid = sms * (per_sm > 0 ? per_sm : 1);
+    if (grid > pairs) grid = pairs;
+    k_c2r_rows_bulk<P, TOut, UP2><<<grid, P::kT, smem, s>>>(a.spec, (TOut*)a.pre, a.tw, P{}, a.dm, pairs, a.scale);
+    return cudaGetLastError();
+}
+template <class P, int PPB> cudaError_t run_bulk(cudaStream_t s, const C2rArgs& a, int, size_t) {
+    const bool up2 = (a.dm.up_w == 2 * a.dm.w);
+    if (a.precision == 2) return up2 ? run_bulk_t<P, __half, true>(s, a) : run_bulk_t<P, __half, false>(s, a);
+    return up2 ? run_bulk_t<P, float, true>(s, a) : run_bulk_t<P, float, false>(s, a);
+}
+
 template <class P, int PPB> void fill(RowImpl* o, const char* name) {
     *o = RowImpl{};
     o->name = name; o->is_static = true;
@@ -35,6 +70,15 @@ template <class P, int PPB> void fill(RowImpl* o, const char* name) {
     o->smem = (size_t)PPB * smem_padded_len(P::kN) * sizeof(float2);
     o->prepare = &prep<P, PPB>;
     o->c2r = &run<P, PPB>;
+    // default: the bulk-copy (mbarrier-prefetched, persistent) kernel; B2R_C2R_BULK=0 selects the
+    // direct-load kernel.  Measured on B200, c2: 44.4 -> 39.1 us stand-alone (profiles/README.md).
+    const char* e = getenv("B2R_C2R_BULK");
+    if (!(e && atoi(e) == 0)) {
+        o->name = "c2r_rows_bulk";
+        o->ppb = 1;
+        o->prepare = &prep_bulk<P>;
+        o->c2r = &run_bulk<P, PPB>;
+    }
 }
 }  // namespace
 
