@@ -41,7 +41,7 @@ def test_unschedulable_sizes_rejected():
         assert eu.schedule(n)[0] is None
 
 
-@pytest.mark.parametrize("n", [256, 512, 1024, 2048, 4096, 1920, 3840, 7680])
+@pytest.mark.parametrize("n", [256, 512, 1024, 2048, 4096, 1920, 3840, 7680, 640, 960, 1280, 2560, 5120])
 def test_static_schedules(n):
     """the ahead-of-time schedules of the BASELINE sizes (b2r_static_sizes.h)"""
     rng = np.random.default_rng(n)

@@ -112,6 +112,12 @@ def test_dynamic_sizes(w, h, up, prec):
     _check(w, h, up, prec, 0.2, "noise")
 
 
+@pytest.mark.parametrize("w,h,prec", [(640, 360, 0), (960, 540, 2), (1280, 720, 0), (2560, 1440, 0)])
+def test_video_sizes_static(w, h, prec):
+    """16:9 sources at 2x with ahead-of-time schedules (radix 3/5 stages, non power-of-two thread counts)"""
+    _check(w, h, 2.0, prec, 0.2, "noise", expect_static=7)
+
+
 def test_forced_dynamic_matches_static(monkeypatch):
     """the any-size kernels on a size that also has a static schedule: same result to rounding"""
     x = vo.synthetic_frame("noise", 256, 128)

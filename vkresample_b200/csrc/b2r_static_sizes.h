@@ -3,8 +3,9 @@
 // The reference JIT-compiles one GLSL shader per axis at plan time (VkFFTPlanAxis,
 // vkFFT.h:6041-7540), so every size gets constants baked in.  The image has no NVRTC, so the same
 // effect is obtained by instantiating the kernel templates here for the sizes of the BASELINE
-// configs (and a few common power-of-two sizes); any other 2^a 3^b 5^c 7^d size runs through the
-// dynamic kernels (b2r_dynamic.cu).
+// configs, a few common power-of-two sizes and the usual 16:9 video sizes at 2x (360p/540p/720p/1440p
+// sources); any other 2^a 3^b 5^c 7^d size runs through the dynamic kernels (b2r_dynamic.cu) at about
+// half the speed -- add a line here and rebuild to promote a size.
 //
 // Row list:  X(N, PPB, T, radices...)   N-point complex transform of one row pair, T threads per
 //            pair, PPB pairs per CTA.  Used for both K1 (N = W) and K7 (N = upW).
@@ -22,7 +23,12 @@
     X(4096, 1, 256, 16, 16, 16)         \
     X(1920, 2, 128, 16, 15, 8)          \
     X(3840, 1, 256, 16, 16, 15)         \
-    X(7680, 1, 512, 16, 16, 15, 2)
+    X(7680, 1, 512, 16, 16, 15, 2)      \
+    X(640, 4, 64, 16, 8, 5)             \
+    X(960, 4, 64, 16, 15, 4)            \
+    X(1280, 2, 96, 16, 16, 5)           \
+    X(2560, 1, 256, 16, 16, 10)         \
+    X(5120, 1, 352, 16, 16, 5, 4)
 
 namespace b2r {
 using ColF128 = StaticFft<128, 16, 16, 8>;
@@ -32,6 +38,14 @@ using ColI2048 = StaticFft<2048, 128, 16, 16, 8>;
 using ColF1080 = StaticFft<1080, 180, 15, 12, 6>;
 using ColI2160 = StaticFft<2160, 180, 15, 12, 12>;
 using ColF2160 = StaticFft<2160, 360, 15, 12, 12>;
+using ColF360 = StaticFft<360, 48, 15, 8, 3>;
+using ColI720 = StaticFft<720, 48, 16, 15, 3>;
+using ColF540 = StaticFft<540, 90, 15, 12, 3>;
+using ColI1080 = StaticFft<1080, 90, 15, 12, 6>;
+using ColF720 = StaticFft<720, 120, 16, 15, 3>;
+using ColI1440 = StaticFft<1440, 120, 16, 15, 6>;
+using ColF1440 = StaticFft<1440, 240, 16, 15, 6>;
+using ColI2880 = StaticFft<2880, 240, 16, 15, 12>;
 using ColI4320 = StaticFft<4320, 360, 16, 15, 6, 3>;
 }  // namespace b2r
 
@@ -39,7 +53,11 @@ using ColI4320 = StaticFft<4320, 360, 16, 15, 6, 3>;
     X(128, 256, 8, ColF128, ColI256)           \
     X(1024, 2048, 4, ColF1024, ColI2048)       \
     X(1080, 2160, 4, ColF1080, ColI2160)       \
-    X(2160, 4320, 2, ColF2160, ColI4320)
+    X(2160, 4320, 2, ColF2160, ColI4320)       \
+    X(360, 720, 8, ColF360, ColI720)           \
+    X(540, 1080, 4, ColF540, ColI1080)         \
+    X(720, 1440, 4, ColF720, ColI1440)         \
+    X(1440, 2880, 4, ColF1440, ColI2880)
 
 // extra tile widths of the c2 column kernel, selectable with B2R_COLS_CC for tuning runs
 #define B2R_STATIC_COLS_TUNING(X)              \
