@@ -331,6 +331,43 @@ def upscale_u8(u8_hwc: np.ndarray, upscale: float = 2.0, sharpen_const: float = 
     return quantise(out)
 
 
+# ------------------------------------------------------ the reference's other path
+def reference_uses_r2c(up_w: int, max_shared_bytes: int = 49152, intel: bool = False) -> bool:
+    """performR2C predicate (VkResample.cpp:1423-1424): the reference silently switches to its C2C
+    path when upW > maxComputeSharedMemorySize / 8 (/4 more on Intel).  48 KB (NVIDIA Vulkan) ->
+    threshold 6144: BASELINE config 5 (upW = 7680) would run C2C there.  The CUDA library keeps R2C
+    semantics at every size; this predicate and ``upscale_frame_c2c`` exist so that the difference can
+    be stated (tests/test_oracle.py::test_c2c_path_differs)."""
+    return not (up_w > max_shared_bytes // 8 // (4 if intel else 1))
+
+
+def upscale_frame_c2c(x: np.ndarray, upscale: float = 2.0, sharpen_const: float = 0.2, workers=None) -> np.ndarray:
+    """The reference's C2C branch restated (float64): complex forward FFT of the real frame, 3-quadrant
+    shift (VkResample.cpp:527-546: both Nyquist lines go to the negative side only), complex inverse
+    with zero ranges [W/2, upW-W/2) x [H/2, upH-H/2) (:1498-1501), CAS on length(vec2) (:884-904) with
+    plane stride upW*upH -- no pad rows: the row below the last row is the next channel's first row
+    (:1598).  NOT pinned by any golden vector (the goldens were produced on the R2C path)."""
+    c, h, w = x.shape
+    plan = make_plan(w, h, upscale)
+    up_w, up_h = plan.up_w, plan.up_h
+    f = _fft.fft2(np.asarray(x, np.float64), axes=(-2, -1), **_kw(workers))
+    b = np.zeros((c, up_h, up_w), np.complex128)
+    hy, hx = h // 2, w // 2
+    b[:, :hy, :hx] = f[:, :hy, :hx]
+    b[:, :hy, up_w - (w - hx):] = f[:, :hy, hx:]
+    b[:, up_h - (h - hy):, :hx] = f[:, hy:, :hx]
+    b[:, up_h - (h - hy):, up_w - (w - hx):] = f[:, hy:, hx:]
+    z = _fft.ifft2(b, axes=(-2, -1), **_kw(workers))
+    t = np.minimum(np.abs(np.float64(_literal(plan.up2)) * z), 1.0)
+    n = up_w * up_h
+    flat = np.concatenate([t.reshape(-1), np.zeros(up_w + 2)])   # beyond the last channel: out of bounds -> 0
+    s = np.float64(_literal(sharpen_const))
+    out = np.empty((c, up_h, up_w))
+    for ch in range(c):
+        _sharpen_rows(flat, ch * n, up_w, up_h, 0, up_h, s, np.float64, out[ch])
+    return out
+
+
 # ------------------------------------------------------------ synthetic frames
 def synthetic_frame(kind: str, w: int, h: int, seed: int = 1234) -> np.ndarray:
     """Deterministic synthetic inputs: 'noise' uniform [0,1), 'smooth'

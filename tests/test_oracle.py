@@ -106,3 +106,19 @@ def test_fp16_mode_within_tolerance_of_fp64():
     o64 = vo.upscale_frame(x, 2.0, 0.2, 2, dtype=np.float64)
     assert o16.dtype == np.float16
     assert np.abs(o16.astype(np.float64) - o64)[:, :-1].max() < 1e-2
+
+
+def test_c2c_path_differs():
+    """The reference switches to a numerically different C2C path for upW > 6144 (NVIDIA Vulkan,
+    48 KB shared memory); this library keeps R2C semantics.  The two paths agree on
+    band-limited content and differ visibly on white noise (x-Nyquist column handling)."""
+    assert vo.reference_uses_r2c(4096) and vo.reference_uses_r2c(6144) and not vo.reference_uses_r2c(7680)
+    assert not vo.reference_uses_r2c(4608, 32768)            # lavapipe: 32 KB -> threshold 4096
+    w, h = 64, 32
+    smooth = vo.synthetic_frame("smooth", w, h)
+    noise = vo.synthetic_frame("noise", w, h)
+    for x, lo, hi in ((smooth, 0.0, 2e-2), (noise, 1e-3, 1.0)):
+        a = vo.upscale_frame(x, 2.0, 0.2, 0, dtype=np.float64)
+        b = vo.upscale_frame_c2c(x, 2.0, 0.2)
+        d = np.abs(a - b)[:, :-1, :].max()     # last row: different memory below the plane in the two layouts
+        assert lo <= d <= hi, d
