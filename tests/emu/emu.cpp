@@ -10,6 +10,9 @@
 #include <cstdio>
 #include <cstring>
 #include <functional>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -23,11 +26,25 @@ thread_local Ctx g_ctx;
 
 struct Dim3 { unsigned x = 1, y = 1, z = 1; };
 
+struct Barriers {
+    std::barrier<> all;
+    std::mutex mu;
+    std::map<int, std::unique_ptr<std::barrier<>>> named;   // created on first use with that id's count
+    explicit Barriers(std::ptrdiff_t n) : all(n) {}
+    std::barrier<>* get(int id, int count) {
+        std::lock_guard<std::mutex> g(mu);
+        auto& b = named[id];
+        if (!b) b = std::make_unique<std::barrier<>>(count);
+        return b.get();
+    }
+};
+
 static void launch(Dim3 grid, Dim3 block, size_t smem_bytes, const std::function<void()>& body) {
     const unsigned nthreads = block.x * block.y;
-    std::barrier bar((std::ptrdiff_t)nthreads);
+    Barriers bar((std::ptrdiff_t)nthreads);
     std::vector<unsigned char> smem(smem_bytes + 64, 0);
-    auto sync_fn = [](void* p) { static_cast<std::barrier<>*>(p)->arrive_and_wait(); };
+    auto sync_fn = [](void* p) { static_cast<Barriers*>(p)->all.arrive_and_wait(); };
+    auto sync_group_fn = [](void* p, int id, int count) { static_cast<Barriers*>(p)->get(id, count)->arrive_and_wait(); };
     auto worker = [&](unsigned t) {
         for (unsigned bz = 0; bz < grid.z; ++bz)
             for (unsigned by = 0; by < grid.y; ++by)
@@ -38,9 +55,9 @@ static void launch(Dim3 grid, Dim3 block, size_t smem_bytes, const std::function
                     c.bdim_x = block.x; c.bdim_y = block.y;
                     c.gdim_x = grid.x; c.gdim_y = grid.y; c.gdim_z = grid.z;
                     c.smem = smem.data();
-                    c.sync = sync_fn; c.sync_arg = &bar;
+                    c.sync = sync_fn; c.sync_arg = &bar; c.sync_group = sync_group_fn;
                     body();
-                    bar.arrive_and_wait();  // CTA boundary: shared memory is reused
+                    bar.all.arrive_and_wait();  // CTA boundary: shared memory is reused
                 }
     };
     std::vector<std::thread> th;
@@ -138,11 +155,23 @@ template <class P, int PPB> static void emu_c2r(FrameCtx& c, const P plan, const
         }
     });
 }
+static int g_cols_grouped = 0;   // opt-in like the product (B2R_COLS_GROUPED=1)
+
 template <class PF, class PI, int CC>
 static void emu_cols(FrameCtx& c, const PF pf, const PI pi, const HostFft& hf, const HostFft& hi) {
     Dim3 grid, block; block.x = CC * hi.desc.threads; grid.x = (c.g.nx + CC - 1) / CC; grid.y = 3;
     const float2 *twf = hf.twiddles.data(), *twi = hi.twiddles.data();
     const float scale = 1.0f / (float)c.g.up_h;
+    if constexpr (PI::kStatic) {
+        if constexpr (PI::kT % 32 == 0 && PF::kStages >= 2 && PI::kStages >= 3) {
+            if (g_cols_grouped) {
+                b2r_emu::launch(grid, block, (size_t)CC * cols_group_stride(c.g.up_h) * sizeof(float2), [&] {
+                    k_cols_grouped<PF, PI, CC>(c.spec1.data(), c.spec2.data(), twf, twi, pf, pi, c.dm, scale);
+                });
+                return;
+            }
+        }
+    }
     b2r_emu::launch(grid, block, smem_padded_len(c.g.up_h * CC) * sizeof(float2), [&] {
         k_cols<PF, PI, CC>(c.spec1.data(), c.spec2.data(), twf, twi, pf, pi, c.dm, scale);
     });
@@ -172,6 +201,7 @@ static void emu_sharpen(const FrameDims dm, int precision, const void* pre, void
 extern "C" {
 
 void b2r_emu_set_c2r_bulk(int on) { g_c2r_bulk = on; }
+void b2r_emu_set_cols_grouped(int on) { g_cols_grouped = on; }
 
 // returns number of stages (>0) or -1; radices[] receives the schedule
 int b2r_emu_schedule(int n, int* radices, int* threads) {

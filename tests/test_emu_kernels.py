@@ -180,3 +180,23 @@ def test_c2r_bulk_copy_variant(prec):
         eu.lib().b2r_emu_set_c2r_bulk(0)
     assert a["used_static"] == 7 and b["used_static"] == 7
     assert np.array_equal(a["pre_flat"], b["pre_flat"]) and np.array_equal(a["out"], b["out"])
+
+
+@pytest.mark.parametrize("prec", [0, 2])
+def test_grouped_column_kernel(prec):
+    """named-barrier column kernel (one thread group per column, per-column shared arrays): a
+    64x512 -> 128x1024 frame whose (512 -> 1024) column pair has a static schedule with T = 64"""
+    w, h = 64, 512
+    plan = vo.make_plan(w, h, 2.0)
+    x = vo.synthetic_frame("noise", w, h).astype(np.float16 if prec == 2 else np.float32)
+    b = eu.frame(x, 2.0, prec, 0.2, plan)                    # CTA-barrier kernel (default)
+    eu.lib().b2r_emu_set_cols_grouped(1)
+    try:
+        a = eu.frame(x, 2.0, prec, 0.2, plan)                # grouped kernel (opt-in)
+    finally:
+        eu.lib().b2r_emu_set_cols_grouped(0)
+    assert a["used_static"] & 2
+    assert np.array_equal(a["spec2"], b["spec2"]) and np.array_equal(a["out"], b["out"])
+    f2 = vo.forward_spectrum(x.astype(np.float64))
+    g = sf.ifft(vo.shift_zero_pad(f2, plan), axis=-2)[:, :, :w // 2 + 1]
+    assert np.abs(a["spec2"] - g).max() <= 2e-6 * np.abs(g).max()

@@ -21,6 +21,7 @@ struct Ctx {
     unsigned char* smem;
     void (*sync)(void*);
     void* sync_arg;
+    void (*sync_group)(void*, int id, int count);   // named barrier `id` over `count` threads
 };
 extern thread_local Ctx g_ctx;
 }  // namespace b2r_emu
@@ -36,6 +37,7 @@ extern thread_local Ctx g_ctx;
 #define B2R_BDIM_Y (b2r_emu::g_ctx.bdim_y)
 #define B2R_GDIM_X (b2r_emu::g_ctx.gdim_x)
 #define B2R_SYNC() (b2r_emu::g_ctx.sync(b2r_emu::g_ctx.sync_arg))
+#define B2R_SYNC_GROUP(id, count) (b2r_emu::g_ctx.sync_group(b2r_emu::g_ctx.sync_arg, (id), (count)))
 #define B2R_SMEM(T) (reinterpret_cast<T*>(b2r_emu::g_ctx.smem))
 #define B2R_LDG(p) (*(p))
 #define B2R_LAUNCH_BOUNDS(t, b)
@@ -52,6 +54,8 @@ extern thread_local Ctx g_ctx;
 #define B2R_BDIM_Y (blockDim.y)
 #define B2R_GDIM_X (gridDim.x)
 #define B2R_SYNC() __syncthreads()
+// named barrier: only the `count` threads (a multiple of 32) that use the same id wait for each other
+#define B2R_SYNC_GROUP(id, count) asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory")
 #define B2R_SMEM(T) (reinterpret_cast<T*>(b2r_dyn_smem))
 #if defined(__CUDA_ARCH__)
 #define B2R_LDG(p) __ldg(p)

@@ -33,6 +33,8 @@
 namespace b2r {
 using ColF128 = StaticFft<128, 16, 16, 8>;
 using ColI256 = StaticFft<256, 16, 16, 16>;
+using ColF512 = StaticFft<512, 64, 16, 8, 4>;
+using ColI1024 = StaticFft<1024, 64, 16, 16, 4>;
 using ColF1024 = StaticFft<1024, 128, 16, 16, 4>;
 using ColI2048 = StaticFft<2048, 128, 16, 16, 8>;
 using ColF1080 = StaticFft<1080, 180, 15, 12, 6>;
@@ -51,6 +53,7 @@ using ColI4320 = StaticFft<4320, 360, 16, 15, 6, 3>;
 
 #define B2R_STATIC_COLS(X)                     \
     X(128, 256, 8, ColF128, ColI256)           \
+    X(512, 1024, 4, ColF512, ColI1024)         \
     X(1024, 2048, 4, ColF1024, ColI2048)       \
     X(1080, 2160, 4, ColF1080, ColI2160)       \
     X(2160, 4320, 2, ColF2160, ColI4320)       \
