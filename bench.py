@@ -186,7 +186,10 @@ def run_b200(args):
     np_dt = np.float16 if prec == 2 else np.float32
 
     # ring of distinct device-resident frames: 2x the L2 (126 MB) worth of inputs + their outputs
+    # a multiple of the lane count: frames that share a buffer then run on the same lane (stream order),
+    # so no two frames in flight ever touch the same output buffer
     ring = max(2, min(args.ring, 16))
+    ring = -(-ring // args.lanes) * args.lanes
     rng = np.random.default_rng(1234 + rank)
     d_in, d_out = [], []
     for i in range(ring):
@@ -233,7 +236,7 @@ def run_b200(args):
     # ---- end to end through the C-ABI with pinned HOST buffers: per frame H2D + frame + D2H, frames
     # rotating over the plan's lanes so that the copies of one frame overlap the kernels of another
     e_frames = max(4, min(F, 16))
-    n_host = max(2, args.lanes + 1)
+    n_host = 2 * args.lanes   # multiple of the lane count (same reason as the device ring)
     h_in = [torch.from_numpy(plan.pack_input(rng.random((3, h, w), dtype=np.float32).astype(np_dt)).view(np.uint8)).pin_memory()
             for _ in range(n_host)]
     h_out = [torch.empty(plan.output_bytes, dtype=torch.uint8).pin_memory() for _ in range(n_host)]

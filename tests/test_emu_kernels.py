@@ -101,6 +101,13 @@ def test_frame_dynamic(w, h, up, prec, cc):
     _check_frame(w, h, up, prec, 0.2, "noise", cc=cc, use_static=False, expect_static=0)
 
 
+@pytest.mark.parametrize("w,h,up,prec", [(4, 4, 2.0, 0), (8, 4, 2.0, 0), (4, 8, 3.0, 0), (6, 10, 2.0, 2),
+                                         (16, 64, 2.0, 0), (10, 6, 5.0, 0)])
+def test_frame_edge_sizes(w, h, up, prec):
+    """minimum size (one radix-4 / radix-2 stage per transform), portrait frames, large factors"""
+    _check_frame(w, h, up, prec, 0.2, "noise", cc=2, use_static=False, expect_static=0)
+
+
 def test_dc_quirk_is_exercised():
     """white noise has a large (ky=H/2, kx=0) term: dropping the reference's complex-DC leak
     (vkFFT.h:2108-2131) would move the pre-sharpen plane by >> 1e-5."""

@@ -118,6 +118,13 @@ def test_video_sizes_static(w, h, prec):
     _check(w, h, 2.0, prec, 0.2, "noise", expect_static=7)
 
 
+@pytest.mark.parametrize("w,h,up,prec", [(4, 4, 2.0, 0), (8, 4, 2.0, 0), (4, 8, 3.0, 0), (6, 10, 2.0, 2),
+                                         (360, 640, 2.0, 0), (1080, 1920, 2.0, 2), (250, 120, 4.0, 0)])
+def test_edge_sizes(w, h, up, prec):
+    """minimum sizes, portrait frames (columns longer than rows), a 4x factor"""
+    _check(w, h, up, prec, 0.2, "noise")
+
+
 def test_forced_dynamic_matches_static(monkeypatch):
     """the any-size kernels on a size that also has a static schedule: same result to rounding"""
     x = vo.synthetic_frame("noise", 256, 128)
