@@ -48,6 +48,11 @@ extern "C" {
 #define B2R_FLAG_NONE 0u
 #define B2R_FLAG_NO_GRAPH 1u       /* launch kernels directly instead of replaying a CUDA graph */
 #define B2R_FLAG_NO_SHARPEN_LITERAL_ROUNDING 2u /* use the raw floats instead of their "%f" text */
+/* Reproduce the reference's C2C branch (performR2C == false, VkResample.cpp:1423-1424: what it runs
+ * when upW > maxComputeSharedMemorySize/8, e.g. upW > 6144 on NVIDIA Vulkan): both Nyquist lines on the
+ * negative side only (:527-546), complex result, sharpen on length(vec2) (:884-904), compact plane
+ * below the sharpen (:1598).  Default (flag clear) is R2C/C2R semantics at every size. */
+#define B2R_FLAG_C2C_PARITY 4u
 
 typedef struct b2r_plan b2r_plan;
 
@@ -65,6 +70,8 @@ typedef struct b2r_plan_info {
     uint32_t column_tile;              /* spectrum columns per CTA in the fused column kernel    */
     uint32_t kernels_per_frame;        /* launches one b2r_execute iteration performs            */
     uint32_t static_kernels;           /* bit0 K1, bit1 columns, bit2 K7: ahead-of-time schedule  */
+    uint32_t c2c_mode;                 /* 1 if created with B2R_FLAG_C2C_PARITY                   */
+    size_t pre_sharpen_plane_stride;   /* elements between planes of the pre-sharpen buffer        */
 } b2r_plan_info;
 
 /* devices_list(), VkResample.cpp:239-268; createInstance..createDevice, :1286-1320 */

@@ -104,6 +104,7 @@ template <class P> static void host_fft_of(HostFft* hf) {
 using b2r_emu::Dim3;
 
 struct FrameCtx {
+    std::vector<float2> nyq;
     Geometry g; FrameDims dm; int precision;
     const void* in; void* out;
     std::vector<float2> spec1, spec2;
@@ -119,10 +120,22 @@ template <class P, int PPB> static void emu_r2c(FrameCtx& c, const P plan, const
         else k_r2c_rows<P, float, PPB>((const float*)c.in, c.spec1.data(), tw, plan, c.dm, pairs);
     });
 }
+static int g_c2c = 0;        // C2C parity mode (B2R_FLAG_C2C_PARITY)
 static int g_c2r_bulk = 0;   // emulate the bulk-copy (persistent) C2R kernel instead of the direct one
 
 template <class P, int PPB> static void emu_c2r(FrameCtx& c, const P plan, const HostFft& hf) {
     int pairs = 3 * c.g.up_h / 2;
+    if (g_c2c) {
+        const int rows = 3 * c.g.up_h;
+        Dim3 grid, block; block.x = hf.desc.threads; block.y = PPB; grid.x = (rows + PPB - 1) / PPB;
+        const float2* tw = hf.twiddles.data();
+        const float scale = 1.0f / (float)c.g.up_w;
+        b2r_emu::launch(grid, block, PPB * smem_padded_len(c.g.up_w) * sizeof(float2), [&] {
+            if (c.precision == 2) k_c2c_rows<P, __half, PPB>(c.spec2.data(), c.nyq.data(), (__half*)c.pre.data(), tw, plan, c.dm, rows, scale);
+            else k_c2c_rows<P, float, PPB>(c.spec2.data(), c.nyq.data(), (float*)c.pre.data(), tw, plan, c.dm, rows, scale);
+        });
+        return;
+    }
     if (g_c2r_bulk) {
         if constexpr (P::kStatic) {
             Dim3 grid, block; block.x = hf.desc.threads; grid.x = 5;   // few persistent CTAs, many trips
@@ -166,14 +179,14 @@ static void emu_cols(FrameCtx& c, const PF pf, const PI pi, const HostFft& hf, c
         if constexpr (PI::kT % 32 == 0 && PF::kStages >= 2 && PI::kStages >= 3) {
             if (g_cols_grouped) {
                 b2r_emu::launch(grid, block, (size_t)CC * cols_group_stride(c.g.up_h) * sizeof(float2), [&] {
-                    k_cols_grouped<PF, PI, CC>(c.spec1.data(), c.spec2.data(), twf, twi, pf, pi, c.dm, scale);
+                    k_cols_grouped<PF, PI, CC>(c.spec1.data(), c.spec2.data(), twf, twi, pf, pi, c.dm, scale, g_c2c ? c.nyq.data() : nullptr);
                 });
                 return;
             }
         }
     }
     b2r_emu::launch(grid, block, smem_padded_len(c.g.up_h * CC) * sizeof(float2), [&] {
-        k_cols<PF, PI, CC>(c.spec1.data(), c.spec2.data(), twf, twi, pf, pi, c.dm, scale);
+        k_cols<PF, PI, CC>(c.spec1.data(), c.spec2.data(), twf, twi, pf, pi, c.dm, scale, g_c2c ? c.nyq.data() : nullptr);
     });
 }
 
@@ -201,6 +214,7 @@ static void emu_sharpen(const FrameDims dm, int precision, const void* pre, void
 extern "C" {
 
 void b2r_emu_set_c2r_bulk(int on) { g_c2r_bulk = on; }
+void b2r_emu_set_c2c(int on) { g_c2c = on; }
 void b2r_emu_set_cols_grouped(int on) { g_cols_grouped = on; }
 
 // returns number of stages (>0) or -1; radices[] receives the schedule
@@ -252,9 +266,10 @@ int b2r_emu_frame(int w, int h, float upscale, int precision, float sharpen_cons
                   void* pre_dump, int* spec_stride_out, int* used_static) {
     FrameCtx c; std::string err;
     Geometry& g = c.g;
-    if (!make_geometry(w, h, upscale, precision, sharpen_const, &g, &err)) { fprintf(stderr, "%s\n", err.c_str()); return -1; }
+    if (!make_geometry(w, h, upscale, precision, sharpen_const, &g, &err, g_c2c != 0)) { fprintf(stderr, "%s\n", err.c_str()); return -1; }
     g.up2 = up2_lit;
     c.dm = dims_of(g); c.precision = precision; c.in = in; c.out = out;
+    c.nyq.assign(3 * (size_t)g.spec_stride, make_float2(0, 0));
     if (spec_stride_out) *spec_stride_out = g.spec_stride;
     c.spec1.assign(g.spec_in_elems(), make_float2(0, 0));
     c.spec2.assign(g.spec_out_elems(), make_float2(0, 0));

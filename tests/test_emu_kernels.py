@@ -207,3 +207,37 @@ def test_grouped_column_kernel(prec):
     f2 = vo.forward_spectrum(x.astype(np.float64))
     g = sf.ifft(vo.shift_zero_pad(f2, plan), axis=-2)[:, :, :w // 2 + 1]
     assert np.abs(a["spec2"] - g).max() <= 2e-6 * np.abs(g).max()
+
+
+@pytest.mark.parametrize("w,h,up,static", [(256, 128, 2.0, True), (48, 20, 1.5, False), (40, 24, 3.0, False)])
+def test_c2c_parity_mode(w, h, up, static):
+    """B2R_FLAG_C2C_PARITY: the reference's C2C branch (complex result, both Nyquist lines on the negative
+    side, sharpen on the magnitude, compact plane) against the oracle's restatement of that branch"""
+    plan = vo.make_plan(w, h, up)
+    x = vo.synthetic_frame("noise", w, h)
+    eu.lib().b2r_emu_set_c2c(1)
+    try:
+        dt = np.float32
+        buf = eu.pack_input(x, dt)
+        out = np.zeros((3, plan.up_h, plan.up_w), dt)
+        n = plan.up_w * plan.up_h
+        pre = np.zeros(3 * n + plan.up_w + 8, dt)
+        import ctypes
+        rc = eu.lib().b2r_emu_frame(w, h, up, 0, 0.2, plan.up2, 4, int(static), buf.ctypes.data, out.ctypes.data,
+                                    None, None, pre.ctypes.data, None, None)
+        assert rc == 0
+    finally:
+        eu.lib().b2r_emu_set_c2c(0)
+    # magnitude plane vs |z| of the oracle's C2C pipeline
+    f = sf.fft2(x.astype(np.float64), axes=(-2, -1))
+    b = np.zeros((3, plan.up_h, plan.up_w), complex)
+    hy, hx = h // 2, w // 2
+    b[:, :hy, :hx] = f[:, :hy, :hx]
+    b[:, :hy, plan.up_w - (w - hx):] = f[:, :hy, hx:]
+    b[:, plan.up_h - (h - hy):, :hx] = f[:, hy:, :hx]
+    b[:, plan.up_h - (h - hy):, plan.up_w - (w - hx):] = f[:, hy:, hx:]
+    mag = np.abs(sf.ifft2(b, axes=(-2, -1)))
+    got = pre[:3 * n].reshape(3, plan.up_h, plan.up_w)
+    assert np.abs(got - mag).max() * plan.up2 <= 1e-5
+    ref = vo.upscale_frame_c2c(x, up, 0.2)
+    assert np.abs(out - ref).max() <= 2e-4

@@ -283,3 +283,33 @@ def test_u8_stream_lanes():
         p.synchronize()
         for s_, b in zip(seq, h_out):
             assert np.array_equal(s_, b.numpy())
+
+
+@pytest.mark.parametrize("w,h,up,prec", [(256, 128, 2.0, 0), (3840, 2160, 2.0, 0), (700, 480, 1.5, 0), (1920, 1080, 2.0, 2)])
+def test_c2c_parity_mode(w, h, up, prec):
+    """B2R_FLAG_C2C_PARITY reproduces the reference's C2C branch -- the path the reference itself takes
+    for upW > 6144 on NVIDIA Vulkan, i.e. BASELINE config 5 (VkResample.cpp:1423-1424) -- against the
+    oracle's restatement of that branch (oracle.upscale_frame_c2c)."""
+    import scipy.fft as sf
+    x = vo.synthetic_frame("smooth" if w > 3000 else "noise", w, h)
+    xin = x.astype(np.float16 if prec == 2 else np.float32)
+    with vb.Plan(w, h, up, prec, 0.2, flags=vb.FLAG_C2C_PARITY) as p:
+        assert p.info.c2c_mode == 1 and p.pre_plane_stride == p.up_w * p.up_h
+        out = p.upscale(xin)
+        mag = p.download_pre_sharpen()
+    f = sf.fft2(xin.astype(np.float64), axes=(-2, -1), workers=WORKERS)
+    b = np.zeros((3, p.up_h, p.up_w), complex)
+    hy, hx = h // 2, w // 2
+    b[:, :hy, :hx] = f[:, :hy, :hx]
+    b[:, :hy, p.up_w - (w - hx):] = f[:, :hy, hx:]
+    b[:, p.up_h - (h - hy):, :hx] = f[:, hy:, :hx]
+    b[:, p.up_h - (h - hy):, p.up_w - (w - hx):] = f[:, hy:, hx:]
+    ref_mag = np.abs(sf.ifft2(b, axes=(-2, -1), workers=WORKERS))
+    e_mag = np.abs(mag.astype(np.float64) - ref_mag).max() * (up * up)
+    ref = vo.upscale_frame_c2c(xin.astype(np.float64), up, 0.2, workers=WORKERS)
+    e2e = np.abs(out.astype(np.float64) - ref).max()
+    print(f"\n[c2c] {w}x{h} x{up} p={prec}: |z|*up2 max-abs {e_mag:.3e}  e2e max-abs {e2e:.3e}")
+    if prec == 0:
+        assert e_mag <= 1e-5 and e2e <= 1e-3
+    else:
+        assert e_mag <= 2e-3 and e2e <= 1e-2

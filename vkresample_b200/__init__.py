@@ -23,6 +23,7 @@ PRECISION_FP32 = 0
 PRECISION_FP16 = 2
 FLAG_NO_GRAPH = 1
 FLAG_NO_SHARPEN_LITERAL_ROUNDING = 2
+FLAG_C2C_PARITY = 4
 
 # every symbol include/b2resample.h declares (checked by tests/test_abi.py)
 EXPORTS = [
@@ -51,6 +52,7 @@ class PlanInfo(ctypes.Structure):
         ("input_bytes", ctypes.c_size_t), ("output_bytes", ctypes.c_size_t), ("device_bytes", ctypes.c_size_t),
         ("n_stages", ctypes.c_uint32 * 4), ("radices", (ctypes.c_uint32 * 8) * 4), ("threads", ctypes.c_uint32 * 4),
         ("column_tile", ctypes.c_uint32), ("kernels_per_frame", ctypes.c_uint32), ("static_kernels", ctypes.c_uint32),
+        ("c2c_mode", ctypes.c_uint32), ("pre_sharpen_plane_stride", ctypes.c_size_t),
     ]
 
 
@@ -161,7 +163,7 @@ class Plan:
 
     @property
     def pre_plane_stride(self) -> int:
-        return (self.up_w + 2) * self.up_h
+        return int(self.info.pre_sharpen_plane_stride)
 
     def pack_input(self, x: np.ndarray, out: Optional[np.ndarray] = None) -> np.ndarray:
         """[3,H,W] array -> the reference's input buffer layout (plane stride (W+2)*H)."""

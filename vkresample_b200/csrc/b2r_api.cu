@@ -66,6 +66,7 @@ struct Lane {
     float2* d_spec1 = nullptr;
     float2* d_spec2 = nullptr;
     cudaEvent_t done = nullptr;
+    float2* d_nyq = nullptr;           // C2C parity mode: y-Nyquist row of the forward column transform
     unsigned char* u8_in = nullptr;    // interleaved u8 staging, allocated on first use of the u8 API
     unsigned char* u8_out = nullptr;
 };
@@ -84,6 +85,8 @@ struct b2r_plan {
     float2* d_spec1 = nullptr;
     float2* d_spec2 = nullptr;
     float2* d_tw = nullptr;
+    float2* d_nyq = nullptr;   // lane 0, C2C parity mode only
+    bool c2c = false;
     FftDesc* d_fd = nullptr;   // 4 descriptors for the dynamic kernels: W, H, upH, upW
     const float2 *tw_w = nullptr, *tw_h = nullptr, *tw_uh = nullptr, *tw_uw = nullptr;
     size_t device_bytes = 0;
@@ -98,7 +101,7 @@ struct b2r_plan {
     std::vector<Lane> extra;   // lanes 1..n-1
     uint32_t next_lane = 0;
     Lane lane(uint32_t i) const {
-        if (i == 0) { Lane l; l.stream = stream; l.d_in = d_in; l.d_pre = d_pre; l.d_out = d_out; l.d_spec1 = d_spec1; l.d_spec2 = d_spec2; l.done = ev1; return l; }
+        if (i == 0) { Lane l; l.stream = stream; l.d_in = d_in; l.d_pre = d_pre; l.d_out = d_out; l.d_spec1 = d_spec1; l.d_spec2 = d_spec2; l.done = ev1; l.d_nyq = d_nyq; return l; }
         return extra[i - 1];
     }
     uint32_t num_lanes() const { return 1 + (uint32_t)extra.size(); }
@@ -120,15 +123,17 @@ int launch_frame(b2r_plan* p, cudaStream_t s, const void* d_in = nullptr, void* 
     float2* spec1 = ln ? ln->d_spec1 : p->d_spec1;
     float2* spec2 = ln ? ln->d_spec2 : p->d_spec2;
     void* pre = ln ? ln->d_pre : p->d_pre;
+    float2* nyq = p->c2c ? (ln ? ln->d_nyq : p->d_nyq) : nullptr;
     if (ev) CU(cudaEventRecord(ev[0], s));
     R2cArgs a1{d_in ? d_in : (ln ? ln->d_in : p->d_in), spec1, p->tw_w, p->d_fd + 0, p->dm, g.precision};
     CU(p->k_r2c.r2c(s, a1, p->k_r2c.sched.threads, p->k_r2c.smem));
     if (ev) CU(cudaEventRecord(ev[1], s));
-    ColsArgs a2{spec1, spec2, p->tw_h, p->tw_uh, p->d_fd + 1, p->d_fd + 2, p->dm, 1.0f / (float)g.up_h};
+    ColsArgs a2{spec1, spec2, p->tw_h, p->tw_uh, p->d_fd + 1, p->d_fd + 2, p->dm, 1.0f / (float)g.up_h, nyq};
     CU(p->k_cols.launch(s, a2, p->k_cols.inv.threads, p->k_cols.smem));
     if (ev) CU(cudaEventRecord(ev[2], s));
-    C2rArgs a3{spec2, pre, p->tw_uw, p->d_fd + 3, p->dm, g.precision, 1.0f / (float)g.up_w};
-    CU(p->k_c2r.c2r(s, a3, p->k_c2r.sched.threads, p->k_c2r.smem));
+    C2rArgs a3{spec2, pre, p->tw_uw, p->d_fd + 3, p->dm, g.precision, 1.0f / (float)g.up_w, nyq};
+    if (p->c2c) CU(p->k_c2r.c2c(s, a3, p->k_c2r.sched.threads, p->k_c2r.smem_c2c));
+    else CU(p->k_c2r.c2r(s, a3, p->k_c2r.sched.threads, p->k_c2r.smem));
     if (ev) CU(cudaEventRecord(ev[3], s));
     int rc = launch_sharpen(p, s, d_out, ln);
     if (rc) return rc;
@@ -208,6 +213,12 @@ int build(b2r_plan* p) {
         return fail(B2R_ERR_UNSUPPORTED, "row transform %d / %d does not fit one CTA", g.w, g.up_w);
     CU(p->k_r2c.prepare(p->k_r2c.smem));
     CU(p->k_c2r.prepare(p->k_c2r.smem));
+    if (p->c2c) {
+        if (!p->k_c2r.is_static) p->k_c2r.smem_c2c = (size_t)p->k_c2r.ppb_c2c * smem_padded_len(g.up_w) * sizeof(float2);
+        if (p->k_c2r.sched.threads * p->k_c2r.ppb_c2c > lim_7 || p->k_c2r.smem_c2c > smem_max)
+            return fail(B2R_ERR_UNSUPPORTED, "row transform %d does not fit one CTA", g.up_w);
+        CU(p->k_c2r.prepare_c2c(p->k_c2r.smem_c2c));
+    }
     CU(p->k_cols.prepare(p->k_cols.smem));
 
     // kernel-side dimensions
@@ -231,6 +242,10 @@ int build(b2r_plan* p) {
     CU(cudaMalloc((void**)&p->d_spec2, b_s2));
     CU(cudaMalloc((void**)&p->d_tw, (n_tw + 1) * sizeof(float2)));
     CU(cudaMalloc((void**)&p->d_fd, 4 * sizeof(FftDesc)));
+    if (p->c2c) {
+        CU(cudaMalloc((void**)&p->d_nyq, 3 * (size_t)g.spec_stride * sizeof(float2)));
+        CU(cudaMemset(p->d_nyq, 0, 3 * (size_t)g.spec_stride * sizeof(float2)));
+    }
     p->device_bytes = b_in + b_pre + b_out + b_s1 + b_s2 + (n_tw + 1) * sizeof(float2) + 4 * sizeof(FftDesc);
     CU(cudaMemset(p->d_in, 0, b_in));
     CU(cudaMemset(p->d_pre, 0, b_pre));  // the plane pad regions stay zero for the plan's lifetime
@@ -296,7 +311,8 @@ int b2r_plan_create(b2r_plan** out, int device, uint32_t w, uint32_t h, float up
     if (precision == 1) return fail(B2R_ERR_UNSUPPORTED, "precision 1 (double) is not supported; use 0 (fp32) or 2 (fp16)");
     Geometry g;
     std::string err;
-    if (!make_geometry((int)w, (int)h, upscale, (int)precision, sharpen, &g, &err))
+    const bool c2c = (flags & B2R_FLAG_C2C_PARITY) != 0;
+    if (!make_geometry((int)w, (int)h, upscale, (int)precision, sharpen, &g, &err, c2c))
         return fail(err.find("not of the form") != std::string::npos ? B2R_ERR_UNSUPPORTED : B2R_ERR_INVALID_ARG, "%s", err.c_str());
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -307,7 +323,7 @@ int b2r_plan_create(b2r_plan** out, int device, uint32_t w, uint32_t h, float up
     CU(cudaSetDevice(device));
     b2r_plan* p = new (std::nothrow) b2r_plan();
     if (!p) return fail(B2R_ERR_NOMEM, "out of host memory");
-    p->device = device; p->flags = flags; p->g = g;
+    p->device = device; p->flags = flags; p->g = g; p->c2c = c2c;
     int rc = build(p);
     if (rc) { std::string keep = g_err; b2r_plan_destroy(p); g_err = keep; return rc; }
     *out = p;
@@ -322,7 +338,7 @@ void b2r_plan_destroy(b2r_plan* p) {
         if (l.stream) { cudaStreamSynchronize(l.stream); cudaStreamDestroy(l.stream); }
         if (l.done) cudaEventDestroy(l.done);
         cudaFree(l.d_in); cudaFree(l.d_pre); cudaFree(l.d_out); cudaFree(l.d_spec1); cudaFree(l.d_spec2);
-        cudaFree(l.u8_in); cudaFree(l.u8_out);
+        cudaFree(l.u8_in); cudaFree(l.u8_out); cudaFree(l.d_nyq);
     }
     cudaFree(p->u8_in0); cudaFree(p->u8_out0);
     p->extra.clear();
@@ -332,7 +348,7 @@ void b2r_plan_destroy(b2r_plan* p) {
     if (p->ev1) cudaEventDestroy(p->ev1);
     if (p->stream) cudaStreamDestroy(p->stream);
     cudaFree(p->d_in); cudaFree(p->d_pre); cudaFree(p->d_out);
-    cudaFree(p->d_spec1); cudaFree(p->d_spec2); cudaFree(p->d_tw); cudaFree(p->d_fd);
+    cudaFree(p->d_spec1); cudaFree(p->d_spec2); cudaFree(p->d_tw); cudaFree(p->d_fd); cudaFree(p->d_nyq);
     delete p;
 }
 
@@ -356,6 +372,8 @@ int b2r_plan_get_info(const b2r_plan* p, b2r_plan_info* info) {
         info->threads[i] = f[i]->desc.threads;
         for (int s = 0; s < f[i]->desc.nstages; ++s) info->radices[i][s] = f[i]->desc.st[s].radix;
     }
+    info->c2c_mode = p->c2c ? 1u : 0u;
+    info->pre_sharpen_plane_stride = g.pre_plane;
     info->column_tile = p->k_cols.cc;
     info->static_kernels = (p->k_r2c.is_static ? 1u : 0u) | (p->k_cols.is_static ? 2u : 0u) | (p->k_c2r.is_static ? 4u : 0u);
     info->kernels_per_frame = p->kernels_per_frame;
@@ -459,6 +477,10 @@ int b2r_plan_set_lanes(b2r_plan* p, uint32_t lanes) {
         CU(cudaMemset(l.d_pre, 0, g.pre_elems * eb));
         CU(cudaMemset(l.d_spec1, 0, g.spec_in_elems() * sizeof(float2)));
         CU(cudaMemset(l.d_spec2, 0, g.spec_out_elems() * sizeof(float2)));
+        if (p->c2c) {
+            CU(cudaMalloc((void**)&l.d_nyq, 3 * (size_t)g.spec_stride * sizeof(float2)));
+            CU(cudaMemset(l.d_nyq, 0, 3 * (size_t)g.spec_stride * sizeof(float2)));
+        }
         p->device_bytes += g.input_bytes() + g.pre_elems * eb + g.output_bytes() +
                            (g.spec_in_elems() + g.spec_out_elems()) * sizeof(float2);
         p->extra.push_back(l);

@@ -41,6 +41,7 @@ extern thread_local Ctx g_ctx;
 #define B2R_SMEM(T) (reinterpret_cast<T*>(b2r_emu::g_ctx.smem))
 #define B2R_LDG(p) (*(p))
 #define B2R_LAUNCH_BOUNDS(t, b)
+inline float sinpif(float x) { return (float)std::sin(3.14159265358979323846 * (double)x); }
 #else
 #define B2R_HD __host__ __device__ __forceinline__
 #define B2R_DEV __device__ __forceinline__

@@ -37,13 +37,28 @@ cudaError_t run_c2r(cudaStream_t s, const C2rArgs& a, int threads, size_t smem) 
         k_c2r_rows<DynFft, float, kDynPPB, false><<<grid, block, smem, s>>>(a.spec, (float*)a.pre, a.tw, DynFft{a.dfd}, a.dm, pairs, a.scale);
     return cudaGetLastError();
 }
+cudaError_t prep_c2c(size_t smem) {
+    if (smem <= 48 * 1024) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(k_c2c_rows<DynFft, float, kDynPPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_c2c_rows<DynFft, __half, kDynPPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+cudaError_t run_c2c(cudaStream_t s, const C2rArgs& a, int threads, size_t smem) {
+    const int rows = 3 * a.dm.up_h;
+    dim3 block(threads, kDynPPB), grid(rows);
+    if (a.precision == 2)
+        k_c2c_rows<DynFft, __half, kDynPPB><<<grid, block, smem, s>>>(a.spec, a.nyq, (__half*)a.pre, a.tw, DynFft{a.dfd}, a.dm, rows, a.scale);
+    else
+        k_c2c_rows<DynFft, float, kDynPPB><<<grid, block, smem, s>>>(a.spec, a.nyq, (float*)a.pre, a.tw, DynFft{a.dfd}, a.dm, rows, a.scale);
+    return cudaGetLastError();
+}
 template <int CC> cudaError_t prep_cols(size_t smem) {
     if (smem <= 48 * 1024) return cudaSuccess;
     return cudaFuncSetAttribute(k_cols<DynFft, DynFft, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
 template <int CC> cudaError_t run_cols(cudaStream_t s, const ColsArgs& a, int threads, size_t smem) {
     dim3 block(threads * CC), grid((a.dm.nx + CC - 1) / CC, 3);
-    k_cols<DynFft, DynFft, CC><<<grid, block, smem, s>>>(a.in, a.out, a.tw_f, a.tw_i, DynFft{a.dfd_f}, DynFft{a.dfd_i}, a.dm, a.scale);
+    k_cols<DynFft, DynFft, CC><<<grid, block, smem, s>>>(a.in, a.out, a.tw_f, a.tw_i, DynFft{a.dfd_f}, DynFft{a.dfd_i}, a.dm, a.scale, a.nyq);
     return cudaGetLastError();
 }
 }  // namespace
@@ -55,6 +70,7 @@ void get_dynamic_r2c(RowImpl* o) {
 void get_dynamic_c2r(RowImpl* o) {
     *o = RowImpl{};
     o->name = "c2r_rows<dynamic>"; o->ppb = kDynPPB; o->prepare = &prep_c2r; o->c2r = &run_c2r;
+    o->c2c = &run_c2c; o->prepare_c2c = &prep_c2c; o->ppb_c2c = kDynPPB;
 }
 void get_dynamic_cols(int cc, ColImpl* o) {
     *o = ColImpl{};

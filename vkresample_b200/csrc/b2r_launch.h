@@ -19,9 +19,11 @@ struct R2cArgs {
 };
 struct ColsArgs {
     const float2* in; float2* out; const float2 *tw_f, *tw_i; const FftDesc *dfd_f, *dfd_i; FrameDims dm; float scale;
+    float2* nyq = nullptr;   // C2C parity mode: receives F[H/2][x] of the forward column transform
 };
 struct C2rArgs {
     const float2* spec; void* pre; const float2* tw; const FftDesc* dfd; FrameDims dm; int precision; float scale;
+    const float2* nyq = nullptr;   // C2C parity mode (c2c launcher only)
 };
 struct SharpenArgs {
     const void* pre; void* out; FrameDims dm; int precision;
@@ -41,6 +43,10 @@ struct RowImpl {       // K1 or K7 resolved for one size
     cudaError_t (*prepare)(size_t smem) = nullptr;   // per-device function attributes
     cudaError_t (*r2c)(cudaStream_t, const R2cArgs&, int ppb, size_t smem) = nullptr;
     cudaError_t (*c2r)(cudaStream_t, const C2rArgs&, int ppb, size_t smem) = nullptr;
+    cudaError_t (*c2c)(cudaStream_t, const C2rArgs&, int threads, size_t smem) = nullptr;   // k_c2c_rows, same schedule
+    cudaError_t (*prepare_c2c)(size_t smem) = nullptr;
+    int ppb_c2c = 1;
+    size_t smem_c2c = 0;
 };
 
 struct ColImpl {       // fused column kernel resolved for one (H, upH) pair

@@ -91,7 +91,8 @@ bool schedule_fft(int n, HostFft* out, std::string* err, int force_threads) {
     return true;
 }
 
-bool make_geometry(int w, int h, float upscale, int precision, float sharpen, Geometry* g, std::string* err) {
+bool make_geometry(int w, int h, float upscale, int precision, float sharpen, Geometry* g, std::string* err,
+                   bool c2c_layout) {
     auto fail = [&](const std::string& m) { if (err) *err = m; return false; };
     if (w < 4 || h < 4 || (w & 1) || (h & 1)) return fail("input width and height must be even and >= 4");
     if (!(upscale >= 1.0f)) return fail("upscale factor must be >= 1");
@@ -110,7 +111,7 @@ bool make_geometry(int w, int h, float upscale, int precision, float sharpen, Ge
     r.neg_shift = r.up_h - h;
     r.up2 = upscale * upscale;
     r.in_row = (size_t)w;            r.in_plane = (size_t)(w + 2) * h;
-    r.pre_row = (size_t)r.up_w;      r.pre_plane = (size_t)(r.up_w + 2) * r.up_h;
+    r.pre_row = (size_t)r.up_w;      r.pre_plane = c2c_layout ? (size_t)r.up_w * r.up_h : (size_t)(r.up_w + 2) * r.up_h;
     r.out_row = (size_t)r.up_w;      r.out_plane = (size_t)r.up_w * r.up_h;
     r.pre_elems = 3 * r.pre_plane + (size_t)r.up_w + 8;
     std::vector<int> tmp;

@@ -54,6 +54,9 @@ struct Geometry {
     size_t spec_out_elems() const { return 3ull * up_h * spec_stride; }
 };
 
-bool make_geometry(int w, int h, float upscale, int precision, float sharpen, Geometry* g, std::string* err);
+// c2c_layout: the C2R/C2C-rows result is stored on a COMPACT plane (stride upW*upH, no pad rows) like the
+// reference's C2C branch (VkResample.cpp:1598) instead of the R2C branch's (upW+2)*upH.
+bool make_geometry(int w, int h, float upscale, int precision, float sharpen, Geometry* g, std::string* err,
+                   bool c2c_layout = false);
 
 }  // namespace b2r

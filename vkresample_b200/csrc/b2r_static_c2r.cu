@@ -61,6 +61,23 @@ template <class P, int PPB> cudaError_t run_bulk(cudaStream_t s, const C2rArgs& 
     return up2 ? run_bulk_t<P, float, true>(s, a) : run_bulk_t<P, float, false>(s, a);
 }
 
+// ---- C2C parity mode rows (k_c2c_rows): same schedule, one complex transform per output row
+template <class P, int PPB> cudaError_t prep_c2c(size_t smem) {
+    if (smem <= 48 * 1024) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(k_c2c_rows<P, float, PPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(k_c2c_rows<P, __half, PPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+template <class P, int PPB> cudaError_t run_c2c(cudaStream_t s, const C2rArgs& a, int, size_t smem) {
+    const int rows = 3 * a.dm.up_h;
+    dim3 block(P::kT, PPB), grid((rows + PPB - 1) / PPB);
+    if (a.precision == 2)
+        k_c2c_rows<P, __half, PPB><<<grid, block, smem, s>>>(a.spec, a.nyq, (__half*)a.pre, a.tw, P{}, a.dm, rows, a.scale);
+    else
+        k_c2c_rows<P, float, PPB><<<grid, block, smem, s>>>(a.spec, a.nyq, (float*)a.pre, a.tw, P{}, a.dm, rows, a.scale);
+    return cudaGetLastError();
+}
+
 template <class P, int PPB> void fill(RowImpl* o, const char* name) {
     *o = RowImpl{};
     o->name = name; o->is_static = true;
@@ -70,6 +87,10 @@ template <class P, int PPB> void fill(RowImpl* o, const char* name) {
     o->smem = (size_t)PPB * smem_padded_len(P::kN) * sizeof(float2);
     o->prepare = &prep<P, PPB>;
     o->c2r = &run<P, PPB>;
+    o->c2c = &run_c2c<P, PPB>;
+    o->prepare_c2c = &prep_c2c<P, PPB>;
+    o->ppb_c2c = PPB;
+    o->smem_c2c = o->smem;
     // default: the bulk-copy (mbarrier-prefetched, persistent) kernel; B2R_C2R_BULK=0 selects the
     // direct-load kernel.  Measured on B200, c2: 44.4 -> 39.1 us stand-alone (profiles/README.md).
     const char* e = getenv("B2R_C2R_BULK");

@@ -13,7 +13,7 @@ template <class PF, class PI, int CC> cudaError_t prep(size_t smem) {
 }
 template <class PF, class PI, int CC> cudaError_t run(cudaStream_t s, const ColsArgs& a, int, size_t smem) {
     dim3 block(PI::kT * CC), grid((a.dm.nx + CC - 1) / CC, 3);
-    k_cols<PF, PI, CC><<<grid, block, smem, s>>>(a.in, a.out, a.tw_f, a.tw_i, PF{}, PI{}, a.dm, a.scale);
+    k_cols<PF, PI, CC><<<grid, block, smem, s>>>(a.in, a.out, a.tw_f, a.tw_i, PF{}, PI{}, a.dm, a.scale, a.nyq);
     return cudaGetLastError();
 }
 template <class PF, class PI, int CC> constexpr bool grouped_ok() {
@@ -30,7 +30,7 @@ template <class PF, class PI, int CC> cudaError_t prep_grouped(size_t smem) {
 template <class PF, class PI, int CC> cudaError_t run_grouped(cudaStream_t s, const ColsArgs& a, int, size_t smem) {
     if constexpr (grouped_ok<PF, PI, CC>()) {
         dim3 block(PI::kT * CC), grid((a.dm.nx + CC - 1) / CC, 3);
-        k_cols_grouped<PF, PI, CC><<<grid, block, smem, s>>>(a.in, a.out, a.tw_f, a.tw_i, PF{}, PI{}, a.dm, a.scale);
+        k_cols_grouped<PF, PI, CC><<<grid, block, smem, s>>>(a.in, a.out, a.tw_f, a.tw_i, PF{}, PI{}, a.dm, a.scale, a.nyq);
         return cudaGetLastError();
     } else {
         return cudaErrorInvalidValue;
