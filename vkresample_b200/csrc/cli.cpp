@@ -174,7 +174,7 @@ static bool write_rgb(const char* path, const unsigned char* rgb, int w, int h) 
 // ------------------------------------------------------------------------------------------- CLI
 struct Config {  // VkResampleConfiguration, VkResample.cpp:45-59
     uint32_t device_id = 0, upload_files = 0, num_iter = 1, precision = 0, num_threads = 1, thread_id = 0;
-    uint32_t num_files = 1, gpus = 1;
+    uint32_t num_files = 1, gpus = 1, c2c = 0;
     float upscale = 1.0f, sharpen = 0.2f;
     const char* input = nullptr;
     const char* output = nullptr;
@@ -206,7 +206,8 @@ static int launch_resample(Config cfg) {
     if (!png::load_rgb(name, &rgb, &w, &h, &err)) { printf("Image not found\n"); return 5; /* VK_INCOMPLETE */ }
 
     b2r_plan* plan = nullptr;
-    int rc = b2r_plan_create(&plan, device, (uint32_t)w, (uint32_t)h, cfg.upscale, cfg.precision, cfg.sharpen, 0);
+    int rc = b2r_plan_create(&plan, device, (uint32_t)w, (uint32_t)h, cfg.upscale, cfg.precision, cfg.sharpen,
+                             cfg.c2c ? B2R_FLAG_C2C_PARITY : B2R_FLAG_NONE);
     if (rc) { printf("Plan creation failed, error code: %d (%s)\n", rc, b2r_last_error()); return rc; }
     b2r_plan_info info;
     b2r_plan_get_info(plan, &info);
@@ -267,7 +268,9 @@ int main(int argc, char* argv[]) {
                "\t-ofolder NAME: output folder, same numbering\n"
                "\t-numfiles X: number of files in the folder\n"
                "\t-numthreads X: number of worker threads, each with its own plan (default 1)\n"
-               "\t-gpus X: (extension) spread the worker threads over X CUDA devices (default 1)\n");
+               "\t-gpus X: (extension) spread the worker threads over X CUDA devices (default 1)\n"
+               "\t-c2c: (extension) reproduce the reference's C2C branch (what VkResample runs when the upscaled width\n"
+               "\t      exceeds its shared-memory limit, e.g. > 6144 on NVIDIA); default is R2C/C2R at every size\n");
         return 0;
     }
     if (find_flag(argv, argv + argc, "-pngcopy")) {  // diagnostic: decode + re-encode (codec self-test, no GPU)
@@ -295,6 +298,7 @@ int main(int argc, char* argv[]) {
     if (need("-d", "%u", &cfg.device_id) || need("-n", "%u", &cfg.num_iter) || need("-p", "%u", &cfg.precision) ||
         need("-s", "%f", &cfg.sharpen) || need("-u", "%f", &cfg.upscale) || need("-gpus", "%u", &cfg.gpus))
         return 1;
+    cfg.c2c = find_flag(argv, argv + argc, "-c2c") ? 1u : 0u;
     if (find_flag(argv, argv + argc, "-ifolder")) {  // batch mode, VkResample.cpp:1893-1957
         cfg.upload_files = 1;
         cfg.ifolder = flag_value(argv, argv + argc, "-ifolder");
