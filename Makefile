@@ -8,7 +8,7 @@ SRC       := vkresample_b200/csrc
 OUT       := vkresample_b200/lib
 OBJ       := build/obj
 CU_SRCS   := b2r_api.cu b2r_static_r2c.cu b2r_static_c2r.cu b2r_static_cols.cu b2r_dynamic.cu b2r_sharpen.cu
-OBJS      := $(addprefix $(OBJ)/,$(CU_SRCS:.cu=.o)) $(OBJ)/b2r_plan.o
+OBJS      := $(addprefix $(OBJ)/,$(CU_SRCS:.cu=.o)) $(OBJ)/b2r_plan.o $(OBJ)/b2r_jit.o
 HDRS      := $(wildcard $(SRC)/*.cuh $(SRC)/*.h) include/b2resample.h
 
 all: $(OUT)/libb2resample.so $(OUT)/b2resample
@@ -21,9 +21,13 @@ $(OBJ)/b2r_plan.o: $(SRC)/b2r_plan.cpp $(HDRS)
 	@mkdir -p $(OBJ)
 	$(NVCC) $(NVFLAGS) -x cu -c $< -o $@
 
+$(OBJ)/b2r_jit.o: $(SRC)/b2r_jit.cpp $(HDRS)
+	@mkdir -p $(OBJ)
+	$(NVCC) $(NVFLAGS) -x cu -c $< -o $@
+
 $(OUT)/libb2resample.so: $(OBJS)
 	@mkdir -p $(OUT)
-	$(NVCC) $(ARCH) -shared -o $@ $(OBJS)
+	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -ldl
 
 $(OUT)/b2resample: $(SRC)/cli.cpp $(OUT)/libb2resample.so include/b2resample.h
 	$(CXX) -std=c++17 -O2 -Iinclude $< -o $@ -L$(OUT) -lb2resample -lz -lpthread -Wl,-rpath,'$$ORIGIN'

@@ -53,6 +53,14 @@ extern "C" {
  * negative side only (:527-546), complex result, sharpen on length(vec2) (:884-904), compact plane
  * below the sharpen (:1598).  Default (flag clear) is R2C/C2R semantics at every size. */
 #define B2R_FLAG_C2C_PARITY 4u
+/* Plan-time JIT (default ON): sizes without an ahead-of-time schedule get statically scheduled kernels
+ * compiled with NVRTC when the plan is created (about a second; the cubin is cached on disk) -- the
+ * counterpart of the reference JIT-compiling GLSL for every plan (vkFFT.h:7446-7521).  If NVRTC or the
+ * driver library cannot be loaded the plan silently uses the any-size kernels (about half the speed;
+ * b2r_plan_info.jit_note says why).  B2R_FLAG_NO_JIT (or B2R_JIT=0 in the environment) selects the
+ * any-size kernels on purpose.  B2R_FLAG_JIT is accepted for compatibility and has no effect. */
+#define B2R_FLAG_JIT 8u
+#define B2R_FLAG_NO_JIT 16u
 
 typedef struct b2r_plan b2r_plan;
 
@@ -70,6 +78,8 @@ typedef struct b2r_plan_info {
     uint32_t column_tile;              /* spectrum columns per CTA in the fused column kernel    */
     uint32_t kernels_per_frame;        /* launches one b2r_execute iteration performs            */
     uint32_t static_kernels;           /* bit0 K1, bit1 columns, bit2 K7: ahead-of-time schedule  */
+    uint32_t jit_kernels;              /* same bits: compiled at plan time (subset of static_kernels) */
+    char jit_note[128];                /* why plan-time JIT was not used, "" otherwise                */
     uint32_t c2c_mode;                 /* 1 if created with B2R_FLAG_C2C_PARITY                   */
     size_t pre_sharpen_plane_stride;   /* elements between planes of the pre-sharpen buffer        */
 } b2r_plan_info;

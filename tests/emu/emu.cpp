@@ -196,7 +196,7 @@ static void emu_sharpen(const FrameDims dm, int precision, const void* pre, void
     const int bx = sharpen_rows_block(dm.up_w);
     if (bx > 0) {
         constexpr int RY = kSharpenRowsPerThread;
-        block.x = bx; grid.x = dm.up_w / 4 / bx; grid.y = (dm.up_h + RY - 1) / RY; grid.z = 3;
+        block.x = bx; grid.x = (dm.up_w / 4 + bx - 1) / bx; grid.y = (dm.up_h + RY - 1) / RY; grid.z = 3;
         b2r_emu::launch(grid, block, 0, [&] {
             if (precision == 2) k_sharpen_rows<__half, RY>((const __half*)pre, (__half*)out, dm);
             else k_sharpen_rows<float, RY>((const float*)pre, (float*)out, dm);

@@ -22,17 +22,18 @@ TOL_E2E_FP16 = 1e-2
 WORKERS = os.cpu_count()
 
 
-def _run(w, h, up, prec, s, kind, seed=1234):
+def _run(w, h, up, prec, s, kind, seed=1234, flags=0):
     plan_o = vo.make_plan(w, h, up)
     x = vo.synthetic_frame(kind, w, h, seed)
     dt = np.float16 if prec == 2 else np.float32
     xin = x.astype(dt)
-    with vb.Plan(w, h, up, prec, s) as p:
+    with vb.Plan(w, h, up, prec, s, flags=flags) as p:
         assert (p.up_w, p.up_h) == (plan_o.up_w, plan_o.up_h)
         out = p.upscale(xin)
         pre = p.download_pre_sharpen()
         sh_only = p.sharpen_host(pre)
-        info = dict(static=p.info.static_kernels, sched=p.radix_schedule(), cc=p.info.column_tile)
+        info = dict(static=p.info.static_kernels, jit=p.info.jit_kernels, note=p.info.jit_note.decode(),
+                    sched=p.radix_schedule(), cc=p.info.column_tile)
     return xin, plan_o, out, pre, sh_only, info
 
 
@@ -42,8 +43,10 @@ def _same_bits(a, b):
     return bool(np.all((a.view(bits) == b.view(bits)) | (np.isnan(a) & np.isnan(b))))
 
 
-def _check(w, h, up, prec, s, kind, expect_static=None, e2e_tol=None):
-    xin, plan_o, out, pre, sh_only, info = _run(w, h, up, prec, s, kind)
+def _check(w, h, up, prec, s, kind, expect_static=None, e2e_tol=None, flags=0, expect_jit=None):
+    xin, plan_o, out, pre, sh_only, info = _run(w, h, up, prec, s, kind, flags=flags)
+    if expect_jit is not None:
+        assert info["jit"] == expect_jit, info
     if expect_static is not None:
         assert info["static"] == expect_static, info
     pre_o = vo.pre_sharpen(xin, plan_o, precision=prec, dtype=np.float64, workers=WORKERS)
@@ -108,8 +111,9 @@ def test_c5_4k_to_8k_fp32():
     (60, 36, 2.0, 0), (48, 20, 1.5, 0), (56, 28, 3.0, 0), (40, 24, 1.0, 0), (36, 20, 2.5, 2),
     (640, 360, 2.0, 0), (1280, 720, 1.5, 0), (700, 490, 2.0, 2), (512, 512, 2.0, 0)])
 def test_dynamic_sizes(w, h, up, prec):
-    """sizes without an ahead-of-time schedule: runtime radix dispatch incl. radix 7"""
-    _check(w, h, up, prec, 0.2, "noise")
+    """sizes without an ahead-of-time schedule through the any-size kernels (B2R_FLAG_NO_JIT): runtime
+    radix dispatch incl. radix 7"""
+    _check(w, h, up, prec, 0.2, "noise", flags=vb.FLAG_NO_JIT, expect_jit=0)
 
 
 @pytest.mark.parametrize("w,h,prec", [(640, 360, 0), (960, 540, 2), (1280, 720, 0), (2560, 1440, 0)])
@@ -121,8 +125,10 @@ def test_video_sizes_static(w, h, prec):
 @pytest.mark.parametrize("w,h,up,prec", [(4, 4, 2.0, 0), (8, 4, 2.0, 0), (4, 8, 3.0, 0), (6, 10, 2.0, 2),
                                          (360, 640, 2.0, 0), (1080, 1920, 2.0, 2), (250, 120, 4.0, 0)])
 def test_edge_sizes(w, h, up, prec):
-    """minimum sizes, portrait frames (columns longer than rows), a 4x factor"""
+    """minimum sizes, portrait frames (columns longer than rows), a 4x factor -- through the plan-time JIT
+    (default) and through the any-size kernels"""
     _check(w, h, up, prec, 0.2, "noise")
+    _check(w, h, up, prec, 0.2, "noise", flags=vb.FLAG_NO_JIT, expect_jit=0)
 
 
 def test_forced_dynamic_matches_static(monkeypatch):
@@ -313,3 +319,22 @@ def test_c2c_parity_mode(w, h, up, prec):
         assert e_mag <= 1e-5 and e2e <= 1e-3
     else:
         assert e_mag <= 2e-3 and e2e <= 1e-2
+
+
+@pytest.mark.parametrize("w,h,up,prec", [(1000, 600, 2.0, 0), (1600, 900, 1.5, 2), (250, 120, 4.0, 0), (2048, 600, 2.0, 0),
+                                         (3000, 2000, 2.0, 0)])
+def test_plan_time_jit(w, h, up, prec, tmp_path, monkeypatch):
+    """sizes without an ahead-of-time schedule get statically scheduled kernels compiled with
+    NVRTC at plan time (like the reference's per-plan GLSL JIT); same parity bars as the built-in sizes.
+    (2048, 600): only the column kernel is missing -> mixed ahead-of-time + JIT plan."""
+    monkeypatch.setenv("B2R_CACHE_DIR", str(tmp_path))
+    with vb.Plan(w, h, up, prec, 0.2, flags=vb.FLAG_NO_JIT) as p0:      # any-size kernels on purpose
+        assert p0.info.jit_kernels == 0
+        ref = p0.upscale(vo.synthetic_frame("noise", w, h).astype(p0.dtype)).copy()
+    _check(w, h, up, prec, 0.2, "noise", expect_static=7, expect_jit=2 if (w, h) == (2048, 600) else 7)   # compiles
+    assert any(f.endswith(".cubin") for f in os.listdir(tmp_path))
+    with vb.Plan(w, h, up, prec, 0.2) as p1:                             # second plan: cubin from the disk cache
+        assert p1.info.static_kernels == 7 and p1.info.jit_kernels != 0
+        out = p1.upscale(vo.synthetic_frame("noise", w, h).astype(p1.dtype))
+    tol = 2e-4 if prec == 0 else 1e-2
+    assert np.abs(out.astype(np.float64) - ref.astype(np.float64)).max() <= tol

@@ -24,6 +24,8 @@ PRECISION_FP16 = 2
 FLAG_NO_GRAPH = 1
 FLAG_NO_SHARPEN_LITERAL_ROUNDING = 2
 FLAG_C2C_PARITY = 4
+FLAG_JIT = 8
+FLAG_NO_JIT = 16
 
 # every symbol include/b2resample.h declares (checked by tests/test_abi.py)
 EXPORTS = [
@@ -52,6 +54,7 @@ class PlanInfo(ctypes.Structure):
         ("input_bytes", ctypes.c_size_t), ("output_bytes", ctypes.c_size_t), ("device_bytes", ctypes.c_size_t),
         ("n_stages", ctypes.c_uint32 * 4), ("radices", (ctypes.c_uint32 * 8) * 4), ("threads", ctypes.c_uint32 * 4),
         ("column_tile", ctypes.c_uint32), ("kernels_per_frame", ctypes.c_uint32), ("static_kernels", ctypes.c_uint32),
+        ("jit_kernels", ctypes.c_uint32), ("jit_note", ctypes.c_char * 128),
         ("c2c_mode", ctypes.c_uint32), ("pre_sharpen_plane_stride", ctypes.c_size_t),
     ]
 

@@ -23,6 +23,7 @@
 #include <algorithm>
 
 #include "../../include/b2resample.h"
+#include "b2r_jit.h"
 #include "b2r_launch.h"
 #include "b2r_plan.h"
 
@@ -98,6 +99,8 @@ struct b2r_plan {
     int kernels_per_frame = 4;
     unsigned char* u8_in0 = nullptr;   // lane 0's u8 staging
     unsigned char* u8_out0 = nullptr;
+    JitModule* jit = nullptr;   // kernels compiled at plan time for sizes without an ahead-of-time build
+    std::string jit_note;       // why JIT was not used (if it was not)
     std::vector<Lane> extra;   // lanes 1..n-1
     uint32_t next_lane = 0;
     Lane lane(uint32_t i) const {
@@ -126,14 +129,14 @@ int launch_frame(b2r_plan* p, cudaStream_t s, const void* d_in = nullptr, void* 
     float2* nyq = p->c2c ? (ln ? ln->d_nyq : p->d_nyq) : nullptr;
     if (ev) CU(cudaEventRecord(ev[0], s));
     R2cArgs a1{d_in ? d_in : (ln ? ln->d_in : p->d_in), spec1, p->tw_w, p->d_fd + 0, p->dm, g.precision};
-    CU(p->k_r2c.r2c(s, a1, p->k_r2c.sched.threads, p->k_r2c.smem));
+    CU(p->k_r2c.r2c(s, a1, p->k_r2c.sched.threads, p->k_r2c.smem, p->k_r2c.ctx));
     if (ev) CU(cudaEventRecord(ev[1], s));
     ColsArgs a2{spec1, spec2, p->tw_h, p->tw_uh, p->d_fd + 1, p->d_fd + 2, p->dm, 1.0f / (float)g.up_h, nyq};
-    CU(p->k_cols.launch(s, a2, p->k_cols.inv.threads, p->k_cols.smem));
+    CU(p->k_cols.launch(s, a2, p->k_cols.inv.threads, p->k_cols.smem, p->k_cols.ctx));
     if (ev) CU(cudaEventRecord(ev[2], s));
     C2rArgs a3{spec2, pre, p->tw_uw, p->d_fd + 3, p->dm, g.precision, 1.0f / (float)g.up_w, nyq};
-    if (p->c2c) CU(p->k_c2r.c2c(s, a3, p->k_c2r.sched.threads, p->k_c2r.smem_c2c));
-    else CU(p->k_c2r.c2r(s, a3, p->k_c2r.sched.threads, p->k_c2r.smem));
+    if (p->c2c) CU(p->k_c2r.c2c(s, a3, p->k_c2r.sched.threads, p->k_c2r.smem_c2c, p->k_c2r.ctx));
+    else CU(p->k_c2r.c2r(s, a3, p->k_c2r.sched.threads, p->k_c2r.smem, p->k_c2r.ctx));
     if (ev) CU(cudaEventRecord(ev[3], s));
     int rc = launch_sharpen(p, s, d_out, ln);
     if (rc) return rc;
@@ -193,8 +196,8 @@ int build(b2r_plan* p) {
         schedule_fft(g.up_h, &p->fuh, &err, tc);
         // column tile: widest of {8,4,2} with <= 512 threads and room for >= 2 CTAs per SM
         int cc = env_int("B2R_COLS_CC", 0);
-        if (cc != 2 && cc != 4 && cc != 8) {
-            cc = 2;
+        if (cc != 1 && cc != 2 && cc != 4 && cc != 8) {
+            cc = (2 * tc <= kDynMaxThreads) ? 2 : 1;   // 1: last resort for very long columns
             for (int cand : {8, 4})
                 if (cand * tc <= kDynMaxThreads && smem_padded_len(g.up_h * cand) * sizeof(float2) <= 100 * 1024) { cc = cand; break; }
         }
@@ -202,6 +205,30 @@ int build(b2r_plan* p) {
         sched_from(p->fh, &p->k_cols.fwd);
         sched_from(p->fuh, &p->k_cols.inv);
         p->k_cols.smem = (size_t)smem_padded_len(g.up_h * p->k_cols.cc) * sizeof(float2);
+    }
+    // ---- plan-time JIT for whatever has no ahead-of-time schedule (the reference JIT-compiles every plan)
+    if (!force_dyn && !(p->flags & B2R_FLAG_NO_JIT) &&
+        (!p->k_r2c.is_static || !p->k_cols.is_static || !p->k_c2r.is_static)) {
+        std::string why;
+        if (jit_available(&why)) {
+            JitRequest rq;
+            sched_from(p->fw, &rq.w); sched_from(p->fh, &rq.h); sched_from(p->fuh, &rq.uh); sched_from(p->fuw, &rq.uw);
+            rq.want_r2c = !p->k_r2c.is_static; rq.want_cols = !p->k_cols.is_static; rq.want_c2r = !p->k_c2r.is_static;
+            rq.precision = g.precision; rq.up2 = (g.up_w == 2 * g.w); rq.c2c = p->c2c; rq.nx = g.nx;
+            rq.cache_only = false;
+            const int tc = rq.uh.threads;
+            rq.cc = (tc <= 32) ? 8 : ((4 * tc <= 1024 && smem_padded_len(g.up_h * 4) * sizeof(float2) <= 110 * 1024) ? 4 : 2);
+            RowImpl jr, jc; ColImpl jcol;
+            if (jit_build(rq, &p->jit, &jr, &jcol, &jc, &why)) {
+                if (rq.want_r2c) p->k_r2c = jr;
+                if (rq.want_cols) p->k_cols = jcol;
+                if (rq.want_c2r) p->k_c2r = jc;
+            } else {
+                p->jit_note = why;
+            }
+        } else {
+            p->jit_note = why;
+        }
     }
     const int lim_c = p->k_cols.is_static ? 1024 : kDynMaxThreads;
     const int lim_1 = p->k_r2c.is_static ? 1024 : kDynMaxThreads, lim_7 = p->k_c2r.is_static ? 1024 : kDynMaxThreads;
@@ -211,15 +238,15 @@ int build(b2r_plan* p) {
     if (p->k_r2c.sched.threads * p->k_r2c.ppb > lim_1 || p->k_c2r.sched.threads * p->k_c2r.ppb > lim_7 ||
         p->k_r2c.smem > smem_max || p->k_c2r.smem > smem_max)
         return fail(B2R_ERR_UNSUPPORTED, "row transform %d / %d does not fit one CTA", g.w, g.up_w);
-    CU(p->k_r2c.prepare(p->k_r2c.smem));
-    CU(p->k_c2r.prepare(p->k_c2r.smem));
+    CU(p->k_r2c.prepare(p->k_r2c.smem, p->k_r2c.ctx));
+    CU(p->k_c2r.prepare(p->k_c2r.smem, p->k_c2r.ctx));
     if (p->c2c) {
         if (!p->k_c2r.is_static) p->k_c2r.smem_c2c = (size_t)p->k_c2r.ppb_c2c * smem_padded_len(g.up_w) * sizeof(float2);
         if (p->k_c2r.sched.threads * p->k_c2r.ppb_c2c > lim_7 || p->k_c2r.smem_c2c > smem_max)
             return fail(B2R_ERR_UNSUPPORTED, "row transform %d does not fit one CTA", g.up_w);
-        CU(p->k_c2r.prepare_c2c(p->k_c2r.smem_c2c));
+        CU(p->k_c2r.prepare_c2c(p->k_c2r.smem_c2c, p->k_c2r.ctx));
     }
-    CU(p->k_cols.prepare(p->k_cols.smem));
+    CU(p->k_cols.prepare(p->k_cols.smem, p->k_cols.ctx));
 
     // kernel-side dimensions
     FrameDims& d = p->dm;
@@ -344,6 +371,8 @@ void b2r_plan_destroy(b2r_plan* p) {
     p->extra.clear();
     if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
     if (p->graph) cudaGraphDestroy(p->graph);
+    jit_destroy(p->jit);
+    p->jit = nullptr;
     if (p->ev0) cudaEventDestroy(p->ev0);
     if (p->ev1) cudaEventDestroy(p->ev1);
     if (p->stream) cudaStreamDestroy(p->stream);
@@ -376,6 +405,8 @@ int b2r_plan_get_info(const b2r_plan* p, b2r_plan_info* info) {
     info->pre_sharpen_plane_stride = g.pre_plane;
     info->column_tile = p->k_cols.cc;
     info->static_kernels = (p->k_r2c.is_static ? 1u : 0u) | (p->k_cols.is_static ? 2u : 0u) | (p->k_c2r.is_static ? 4u : 0u);
+    info->jit_kernels = (p->k_r2c.is_jit ? 1u : 0u) | (p->k_cols.is_jit ? 2u : 0u) | (p->k_c2r.is_jit ? 4u : 0u);
+    snprintf(info->jit_note, sizeof info->jit_note, "%s", p->jit_note.c_str());
     info->kernels_per_frame = p->kernels_per_frame;
     return B2R_SUCCESS;
 }

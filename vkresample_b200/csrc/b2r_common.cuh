@@ -8,10 +8,25 @@
 //     container.  It is test infrastructure; the product never links it and has no CPU fallback.
 #pragma once
 
+#if defined(__CUDACC_RTC__)
+// NVRTC (plan-time JIT of schedules for sizes without an ahead-of-time instantiation, b2r_jit.cpp):
+// no host standard library -- take what the kernels need from libcu++ and the compiler built-ins.
+#include <cuda_fp16.h>
+#include <cuda/std/type_traits>
+#include <cuda/std/cstdint>
+namespace std { using ::cuda::std::integral_constant; }
+#ifndef INFINITY
+#define INFINITY __int_as_float(0x7f800000)
+#endif
+#ifndef NAN
+#define NAN __int_as_float(0x7fffffff)
+#endif
+#else
 #include <cuda_runtime.h>
 #include <cuda_fp16.h>
 #include <cstdint>
 #include <type_traits>
+#endif
 
 #if defined(B2R_HOST_EMU)
 #include <cmath>

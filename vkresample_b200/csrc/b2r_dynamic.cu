@@ -7,13 +7,13 @@ namespace b2r {
 namespace {
 constexpr int kDynPPB = 1;
 
-cudaError_t prep_r2c(size_t smem) {
+cudaError_t prep_r2c(size_t smem, const void*) {
     if (smem <= 48 * 1024) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(k_r2c_rows<DynFft, float, kDynPPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_r2c_rows<DynFft, __half, kDynPPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
-cudaError_t run_r2c(cudaStream_t s, const R2cArgs& a, int threads, size_t smem) {
+cudaError_t run_r2c(cudaStream_t s, const R2cArgs& a, int threads, size_t smem, const void*) {
     const int pairs = 3 * a.dm.h / 2;
     dim3 block(threads, kDynPPB), grid(pairs);
     if (a.precision == 2)
@@ -22,13 +22,13 @@ cudaError_t run_r2c(cudaStream_t s, const R2cArgs& a, int threads, size_t smem) 
         k_r2c_rows<DynFft, float, kDynPPB><<<grid, block, smem, s>>>((const float*)a.in, a.spec, a.tw, DynFft{a.dfd}, a.dm, pairs);
     return cudaGetLastError();
 }
-cudaError_t prep_c2r(size_t smem) {
+cudaError_t prep_c2r(size_t smem, const void*) {
     if (smem <= 48 * 1024) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(k_c2r_rows<DynFft, float, kDynPPB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_c2r_rows<DynFft, __half, kDynPPB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
-cudaError_t run_c2r(cudaStream_t s, const C2rArgs& a, int threads, size_t smem) {
+cudaError_t run_c2r(cudaStream_t s, const C2rArgs& a, int threads, size_t smem, const void*) {
     const int pairs = 3 * a.dm.up_h / 2;
     dim3 block(threads, kDynPPB), grid(pairs);
     if (a.precision == 2)
@@ -37,13 +37,13 @@ cudaError_t run_c2r(cudaStream_t s, const C2rArgs& a, int threads, size_t smem) 
         k_c2r_rows<DynFft, float, kDynPPB, false><<<grid, block, smem, s>>>(a.spec, (float*)a.pre, a.tw, DynFft{a.dfd}, a.dm, pairs, a.scale);
     return cudaGetLastError();
 }
-cudaError_t prep_c2c(size_t smem) {
+cudaError_t prep_c2c(size_t smem, const void*) {
     if (smem <= 48 * 1024) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(k_c2c_rows<DynFft, float, kDynPPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_c2c_rows<DynFft, __half, kDynPPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
-cudaError_t run_c2c(cudaStream_t s, const C2rArgs& a, int threads, size_t smem) {
+cudaError_t run_c2c(cudaStream_t s, const C2rArgs& a, int threads, size_t smem, const void*) {
     const int rows = 3 * a.dm.up_h;
     dim3 block(threads, kDynPPB), grid(rows);
     if (a.precision == 2)
@@ -52,11 +52,11 @@ cudaError_t run_c2c(cudaStream_t s, const C2rArgs& a, int threads, size_t smem) 
         k_c2c_rows<DynFft, float, kDynPPB><<<grid, block, smem, s>>>(a.spec, a.nyq, (float*)a.pre, a.tw, DynFft{a.dfd}, a.dm, rows, a.scale);
     return cudaGetLastError();
 }
-template <int CC> cudaError_t prep_cols(size_t smem) {
+template <int CC> cudaError_t prep_cols(size_t smem, const void*) {
     if (smem <= 48 * 1024) return cudaSuccess;
     return cudaFuncSetAttribute(k_cols<DynFft, DynFft, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
-template <int CC> cudaError_t run_cols(cudaStream_t s, const ColsArgs& a, int threads, size_t smem) {
+template <int CC> cudaError_t run_cols(cudaStream_t s, const ColsArgs& a, int threads, size_t smem, const void*) {
     dim3 block(threads * CC), grid((a.dm.nx + CC - 1) / CC, 3);
     k_cols<DynFft, DynFft, CC><<<grid, block, smem, s>>>(a.in, a.out, a.tw_f, a.tw_i, DynFft{a.dfd_f}, DynFft{a.dfd_i}, a.dm, a.scale, a.nyq);
     return cudaGetLastError();
@@ -77,6 +77,7 @@ void get_dynamic_cols(int cc, ColImpl* o) {
     o->name = "cols<dynamic>"; o->cc = cc;
     if (cc == 8) { o->prepare = &prep_cols<8>; o->launch = &run_cols<8>; }
     else if (cc == 4) { o->prepare = &prep_cols<4>; o->launch = &run_cols<4>; }
+    else if (cc == 1) { o->prepare = &prep_cols<1>; o->launch = &run_cols<1>; }
     else { o->cc = 2; o->prepare = &prep_cols<2>; o->launch = &run_cols<2>; }
 }
 }  // namespace b2r

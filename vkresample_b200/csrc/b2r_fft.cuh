@@ -17,7 +17,9 @@
 
 #include "b2r_common.cuh"
 
+#if !defined(__CUDACC_RTC__)
 #include <cmath>
+#endif
 
 namespace b2r {
 

@@ -1,0 +1,348 @@
+// b2r_jit.cpp -- plan-time JIT of statically scheduled kernels for sizes that have no ahead-of-time
+// instantiation (b2r_static_sizes.h).
+//
+// The reference builds its FFT plan by generating GLSL per axis and compiling it with glslang at plan
+// time (shaderGenVkFFT vkFFT.h:4495-4642, compile :7446-7521), so every size runs code with its
+// constants baked in.  This is the B200 counterpart: the kernel templates of b2r_kernels.cuh are
+// instantiated for the plan's exact schedule (StaticFft<N, T, radices...>) with NVRTC for sm_100a,
+// loaded through the driver API, and launched exactly like the ahead-of-time instantiations.
+// libnvrtc and libcuda are dlopen()ed on first use, so the library has no link-time dependency on
+// them; if either is missing (or B2R_JIT=0) the plan falls back to the dynamic kernels.
+// Compiled cubins are cached under $B2R_CACHE_DIR (default ~/.cache/b2resample).
+#include "b2r_jit.h"
+
+#include <algorithm>
+
+#include <dlfcn.h>
+#include <sys/stat.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <mutex>
+#include <sstream>
+#include <vector>
+
+namespace b2r {
+namespace {
+
+// ---- minimal driver-API / NVRTC surface, resolved at run time ------------------------------------
+typedef int CUresult;
+typedef struct CUmod_st* CUmodule;
+typedef struct CUfunc_st* CUfunction;
+typedef struct CUstream_st* CUstream;
+typedef struct _nvrtcProgram* nvrtcProgram;
+constexpr int CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES = 8;
+
+struct Api {
+    bool ok = false;
+    std::string why;
+    CUresult (*cuModuleLoadData)(CUmodule*, const void*) = nullptr;
+    CUresult (*cuModuleUnload)(CUmodule) = nullptr;
+    CUresult (*cuModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+    CUresult (*cuFuncSetAttribute)(CUfunction, int, int) = nullptr;
+    CUresult (*cuLaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream,
+                               void**, void**) = nullptr;
+    CUresult (*cuOccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t) = nullptr;
+    CUresult (*cuGetErrorString)(CUresult, const char**) = nullptr;
+    int (*nvrtcCreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+    int (*nvrtcDestroyProgram)(nvrtcProgram*) = nullptr;
+    int (*nvrtcCompileProgram)(nvrtcProgram, int, const char* const*) = nullptr;
+    int (*nvrtcAddNameExpression)(nvrtcProgram, const char*) = nullptr;
+    int (*nvrtcGetLoweredName)(nvrtcProgram, const char*, const char**) = nullptr;
+    int (*nvrtcGetCUBINSize)(nvrtcProgram, size_t*) = nullptr;
+    int (*nvrtcGetCUBIN)(nvrtcProgram, char*) = nullptr;
+    int (*nvrtcGetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
+    int (*nvrtcGetProgramLog)(nvrtcProgram, char*) = nullptr;
+    int (*nvrtcVersion)(int*, int*) = nullptr;
+};
+
+template <class F> bool sym(void* lib, const char* name, F* out) {
+    *out = reinterpret_cast<F>(dlsym(lib, name));
+    return *out != nullptr;
+}
+
+Api& api() {
+    static Api a;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* cu = dlopen("libcuda.so.1", RTLD_NOW | RTLD_GLOBAL);
+        if (!cu) { a.why = "libcuda.so.1 not found"; return; }
+        void* rtc = nullptr;
+        std::vector<std::string> cands;
+        if (const char* e = getenv("B2R_NVRTC")) cands.push_back(e);
+        if (const char* e = getenv("CUDA_HOME")) cands.push_back(std::string(e) + "/lib64/libnvrtc.so.12");
+        cands.insert(cands.end(), {"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so", "libnvrtc.so"});
+        for (const auto& c : cands)
+            if ((rtc = dlopen(c.c_str(), RTLD_NOW))) break;
+        if (!rtc) { a.why = "libnvrtc.so.12 not found (set B2R_NVRTC or CUDA_HOME)"; return; }
+        bool ok = sym(cu, "cuModuleLoadData", &a.cuModuleLoadData) && sym(cu, "cuModuleUnload", &a.cuModuleUnload) &&
+                  sym(cu, "cuModuleGetFunction", &a.cuModuleGetFunction) && sym(cu, "cuFuncSetAttribute", &a.cuFuncSetAttribute) &&
+                  sym(cu, "cuLaunchKernel", &a.cuLaunchKernel) &&
+                  sym(cu, "cuOccupancyMaxActiveBlocksPerMultiprocessor", &a.cuOccupancyMaxActiveBlocksPerMultiprocessor) &&
+                  sym(cu, "cuGetErrorString", &a.cuGetErrorString) &&
+                  sym(rtc, "nvrtcCreateProgram", &a.nvrtcCreateProgram) && sym(rtc, "nvrtcDestroyProgram", &a.nvrtcDestroyProgram) &&
+                  sym(rtc, "nvrtcCompileProgram", &a.nvrtcCompileProgram) && sym(rtc, "nvrtcAddNameExpression", &a.nvrtcAddNameExpression) &&
+                  sym(rtc, "nvrtcGetLoweredName", &a.nvrtcGetLoweredName) && sym(rtc, "nvrtcGetCUBINSize", &a.nvrtcGetCUBINSize) &&
+                  sym(rtc, "nvrtcGetCUBIN", &a.nvrtcGetCUBIN) && sym(rtc, "nvrtcGetProgramLogSize", &a.nvrtcGetProgramLogSize) &&
+                  sym(rtc, "nvrtcGetProgramLog", &a.nvrtcGetProgramLog) && sym(rtc, "nvrtcVersion", &a.nvrtcVersion);
+        if (!ok) { a.why = "a driver / NVRTC entry point is missing"; return; }
+        a.ok = true;
+    });
+    return a;
+}
+
+cudaError_t cu2rt(CUresult r) { return r == 0 ? cudaSuccess : cudaErrorLaunchFailure; }
+
+std::string type_of(const Schedule& s) {
+    std::ostringstream o;
+    o << "b2r::StaticFft<" << s.n << ", " << s.threads;
+    for (int i = 0; i < s.nst; ++i) o << ", " << s.radices[i];
+    o << ">";
+    return o.str();
+}
+
+std::string this_library_dir() {
+    Dl_info info;
+    if (dladdr((const void*)&this_library_dir, &info) && info.dli_fname) {
+        std::string p = info.dli_fname;
+        size_t k = p.rfind('/');
+        return k == std::string::npos ? "." : p.substr(0, k);
+    }
+    return ".";
+}
+
+uint64_t fnv(const std::string& s, uint64_t h = 1469598103934665603ull) {
+    for (unsigned char c : s) { h ^= c; h *= 1099511628211ull; }
+    return h;
+}
+std::string slurp(const std::string& path) {
+    std::ifstream f(path, std::ios::binary);
+    std::stringstream ss;
+    ss << f.rdbuf();
+    return ss.str();
+}
+std::string cache_dir() {
+    if (const char* e = getenv("B2R_CACHE_DIR")) return e;
+    const char* home = getenv("HOME");
+    return std::string(home ? home : "/tmp") + "/.cache/b2resample";
+}
+void mkdirs(const std::string& p) {
+    for (size_t i = 1; i <= p.size(); ++i)
+        if (i == p.size() || p[i] == '/') mkdir(p.substr(0, i).c_str(), 0755);
+}
+
+// per-plan state: one module with the kernels this plan needs
+struct RowCtx { JitModule* m; CUfunction fn = nullptr, fn_c2c = nullptr; int threads = 0, ppb = 1; bool bulk = false; int sms = 0; };
+struct ColCtx { JitModule* m; CUfunction fn = nullptr; int threads = 0, cc = 4; };
+
+}  // namespace
+
+struct JitModule {
+    CUmodule mod = nullptr;
+    RowCtx r2c, c2r;
+    ColCtx cols;
+};
+
+bool jit_available(std::string* why) {
+    const char* e = getenv("B2R_JIT");
+    if (e && atoi(e) == 0) { if (why) *why = "disabled by B2R_JIT=0"; return false; }
+    Api& a = api();
+    if (!a.ok && why) *why = a.why;
+    return a.ok;
+}
+
+void jit_destroy(JitModule* m) {
+    if (!m) return;
+    if (m->mod && api().ok) api().cuModuleUnload(m->mod);
+    delete m;
+}
+
+// ---- launch trampolines (the same shapes as the ahead-of-time launchers) --------------------------
+namespace {
+cudaError_t prep_row(size_t smem, const void* ctx) {
+    const RowCtx* k = static_cast<const RowCtx*>(ctx);
+    if (smem > 48 * 1024) return cu2rt(api().cuFuncSetAttribute(k->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem));
+    return cudaSuccess;
+}
+cudaError_t prep_row_c2c(size_t smem, const void* ctx) {
+    const RowCtx* k = static_cast<const RowCtx*>(ctx);
+    if (smem > 48 * 1024) return cu2rt(api().cuFuncSetAttribute(k->fn_c2c, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem));
+    return cudaSuccess;
+}
+cudaError_t prep_col(size_t smem, const void* ctx) {
+    const ColCtx* k = static_cast<const ColCtx*>(ctx);
+    if (smem > 48 * 1024) return cu2rt(api().cuFuncSetAttribute(k->fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem));
+    return cudaSuccess;
+}
+cudaError_t run_r2c(cudaStream_t s, const R2cArgs& a, int, size_t smem, const void* ctx) {
+    const RowCtx* k = static_cast<const RowCtx*>(ctx);
+    int pairs = 3 * a.dm.h / 2;
+    char plan = 0;
+    void* args[] = {(void*)&a.in, (void*)&a.spec, (void*)&a.tw, &plan, (void*)&a.dm, &pairs};
+    return cu2rt(api().cuLaunchKernel(k->fn, (pairs + k->ppb - 1) / k->ppb, 1, 1, k->threads, k->ppb, 1, (unsigned)smem,
+                                      (CUstream)s, args, nullptr));
+}
+cudaError_t run_c2r(cudaStream_t s, const C2rArgs& a, int, size_t smem, const void* ctx) {
+    const RowCtx* k = static_cast<const RowCtx*>(ctx);
+    int pairs = 3 * a.dm.up_h / 2;
+    char plan = 0;
+    float scale = a.scale;
+    void* args[] = {(void*)&a.spec, (void*)&a.pre, (void*)&a.tw, &plan, (void*)&a.dm, &pairs, &scale};
+    unsigned grid = (unsigned)((pairs + k->ppb - 1) / k->ppb), by = (unsigned)k->ppb;
+    if (k->bulk) {   // persistent: one CTA per resident slot
+        int per_sm = 0;
+        if (api().cuOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k->fn, k->threads, smem) != 0 || per_sm < 1) per_sm = 1;
+        grid = (unsigned)std::min(pairs, k->sms * per_sm);
+        by = 1;
+    }
+    return cu2rt(api().cuLaunchKernel(k->fn, grid, 1, 1, k->threads, by, 1, (unsigned)smem, (CUstream)s, args, nullptr));
+}
+cudaError_t run_c2c(cudaStream_t s, const C2rArgs& a, int, size_t smem, const void* ctx) {
+    const RowCtx* k = static_cast<const RowCtx*>(ctx);
+    int rows = 3 * a.dm.up_h;
+    char plan = 0;
+    float scale = a.scale;
+    void* args[] = {(void*)&a.spec, (void*)&a.nyq, (void*)&a.pre, (void*)&a.tw, &plan, (void*)&a.dm, &rows, &scale};
+    return cu2rt(api().cuLaunchKernel(k->fn_c2c, (rows + k->ppb - 1) / k->ppb, 1, 1, k->threads, k->ppb, 1, (unsigned)smem,
+                                      (CUstream)s, args, nullptr));
+}
+cudaError_t run_cols(cudaStream_t s, const ColsArgs& a, int, size_t smem, const void* ctx) {
+    const ColCtx* k = static_cast<const ColCtx*>(ctx);
+    char pf = 0, pi = 0;
+    float scale = a.scale;
+    void* args[] = {(void*)&a.in, (void*)&a.out, (void*)&a.tw_f, (void*)&a.tw_i, &pf, &pi, (void*)&a.dm, &scale, (void*)&a.nyq};
+    return cu2rt(api().cuLaunchKernel(k->fn, (a.dm.nx + k->cc - 1) / k->cc, 3, 1, k->threads * k->cc, 1, 1, (unsigned)smem,
+                                      (CUstream)s, args, nullptr));
+}
+}  // namespace
+
+bool jit_build(const JitRequest& rq, JitModule** out_mod, RowImpl* r2c, ColImpl* cols, RowImpl* c2r, std::string* err) {
+    Api& a = api();
+    if (!a.ok) { *err = a.why; return false; }
+    const std::string csrc = this_library_dir() + "/../csrc";
+    const std::string hdr = slurp(csrc + "/b2r_kernels.cuh") + slurp(csrc + "/b2r_fft.cuh") + slurp(csrc + "/b2r_common.cuh");
+    if (hdr.empty()) { *err = "kernel headers not found next to the library (" + csrc + ")"; return false; }
+
+    // ---- source: explicit instantiations of exactly the kernels this plan launches
+    const char* tin = rq.precision == 2 ? "__half" : "float";
+    std::vector<std::string> names;   // name expressions, in the order r2c, cols, c2r, c2c
+    const int ppb_w = std::max(1, std::min(8, 256 / rq.w.threads));
+    const int ppb_uw = std::max(1, std::min(8, 256 / rq.uw.threads));
+    if (rq.want_r2c) {
+        std::ostringstream n;
+        n << "b2r::k_r2c_rows<" << type_of(rq.w) << ", " << tin << ", " << ppb_w << ">";
+        names.push_back(n.str());
+    }
+    if (rq.want_cols) {
+        std::ostringstream n;
+        n << "b2r::k_cols<" << type_of(rq.h) << ", " << type_of(rq.uh) << ", " << rq.cc << ">";
+        names.push_back(n.str());
+    }
+    if (rq.want_c2r) {
+        std::ostringstream n;
+        n << "b2r::k_c2r_rows_bulk<" << type_of(rq.uw) << ", " << tin << ", " << (rq.up2 ? "true" : "false") << ">";
+        names.push_back(n.str());
+        if (rq.c2c) {
+            std::ostringstream m;
+            m << "b2r::k_c2c_rows<" << type_of(rq.uw) << ", " << tin << ", " << ppb_uw << ">";
+            names.push_back(m.str());
+        }
+    }
+    // name expressions instantiate the templates; the source only has to bring the templates in
+    std::string source = "#include \"b2r_kernels.cuh\"\n";
+    for (const auto& n : names) source += "// " + n + "\n";
+
+    int vmaj = 0, vmin = 0;
+    a.nvrtcVersion(&vmaj, &vmin);
+    const uint64_t key = fnv(hdr, fnv(source + std::to_string(vmaj * 100 + vmin)));
+    char keyhex[32];
+    snprintf(keyhex, sizeof keyhex, "%016llx", (unsigned long long)key);
+    const std::string cpath = cache_dir() + "/" + keyhex + ".cubin", npath = cache_dir() + "/" + keyhex + ".names";
+
+    std::string cubin = slurp(cpath);
+    std::vector<std::string> lowered;
+    if (!cubin.empty()) {
+        std::istringstream nf(slurp(npath));
+        std::string line;
+        while (std::getline(nf, line)) if (!line.empty()) lowered.push_back(line);
+        if (lowered.size() != names.size()) { cubin.clear(); lowered.clear(); }
+    }
+    if (cubin.empty()) {
+        if (rq.cache_only) { *err = "no cached JIT build for this size"; return false; }
+        nvrtcProgram prog = nullptr;
+        if (a.nvrtcCreateProgram(&prog, source.c_str(), "b2r_jit.cu", 0, nullptr, nullptr) != 0) { *err = "nvrtcCreateProgram failed"; return false; }
+        for (const auto& n : names) a.nvrtcAddNameExpression(prog, n.c_str());
+        const std::string inc1 = "-I" + csrc;
+        std::string cuda_inc = "-I/usr/local/cuda/include";
+        if (const char* e = getenv("CUDA_HOME")) cuda_inc = std::string("-I") + e + "/include";
+        const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", inc1.c_str(), cuda_inc.c_str(), "-default-device",
+                              "-lineinfo", "-diag-suppress=550"};
+        const int rc = a.nvrtcCompileProgram(prog, 7, opts);
+        if (rc != 0) {
+            size_t ls = 0;
+            a.nvrtcGetProgramLogSize(prog, &ls);
+            std::string log(ls, 0);
+            if (ls) a.nvrtcGetProgramLog(prog, &log[0]);
+            *err = "NVRTC compilation failed: " + log.substr(0, 400);
+            a.nvrtcDestroyProgram(&prog);
+            return false;
+        }
+        for (const auto& n : names) {
+            const char* ln = nullptr;
+            a.nvrtcGetLoweredName(prog, n.c_str(), &ln);
+            lowered.push_back(ln ? ln : "");
+        }
+        size_t cs = 0;
+        a.nvrtcGetCUBINSize(prog, &cs);
+        cubin.resize(cs);
+        a.nvrtcGetCUBIN(prog, &cubin[0]);
+        a.nvrtcDestroyProgram(&prog);
+        mkdirs(cache_dir());
+        std::ofstream(cpath, std::ios::binary).write(cubin.data(), (std::streamsize)cubin.size());
+        std::ofstream nf(npath);
+        for (const auto& l : lowered) nf << l << "\n";
+    }
+
+    JitModule* m = new JitModule();
+    if (a.cuModuleLoadData(&m->mod, cubin.data()) != 0) { *err = "cuModuleLoadData failed"; delete m; return false; }
+    size_t idx = 0;
+    auto get = [&](CUfunction* f) { return a.cuModuleGetFunction(f, m->mod, lowered[idx++].c_str()) == 0; };
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    bool ok = true;
+    if (rq.want_r2c) {
+        m->r2c.m = m; m->r2c.threads = rq.w.threads; m->r2c.ppb = ppb_w;
+        ok = ok && get(&m->r2c.fn);
+        *r2c = RowImpl{};
+        r2c->name = "r2c_rows<jit>"; r2c->is_static = true; r2c->is_jit = true; r2c->sched = rq.w; r2c->ppb = ppb_w;
+        r2c->smem = (size_t)ppb_w * smem_padded_len(rq.w.n) * sizeof(float2);
+        r2c->ctx = &m->r2c; r2c->prepare = &prep_row; r2c->r2c = &run_r2c;
+    }
+    if (rq.want_cols) {
+        m->cols.m = m; m->cols.threads = rq.uh.threads; m->cols.cc = rq.cc;
+        ok = ok && get(&m->cols.fn);
+        *cols = ColImpl{};
+        cols->name = "cols<jit>"; cols->is_static = true; cols->is_jit = true; cols->fwd = rq.h; cols->inv = rq.uh; cols->cc = rq.cc;
+        cols->smem = (size_t)smem_padded_len(rq.uh.n * rq.cc) * sizeof(float2);
+        cols->ctx = &m->cols; cols->prepare = &prep_col; cols->launch = &run_cols;
+    }
+    if (rq.want_c2r) {
+        m->c2r.m = m; m->c2r.threads = rq.uw.threads; m->c2r.ppb = ppb_uw; m->c2r.bulk = true; m->c2r.sms = sms;
+        ok = ok && get(&m->c2r.fn);
+        if (rq.c2c) ok = ok && get(&m->c2r.fn_c2c);
+        *c2r = RowImpl{};
+        c2r->name = "c2r_rows_bulk<jit>"; c2r->is_static = true; c2r->is_jit = true; c2r->sched = rq.uw; c2r->ppb = 1;
+        c2r->smem = c2r_bulk_smem_bytes(rq.uw.n, rq.nx);
+        c2r->ctx = &m->c2r; c2r->prepare = &prep_row; c2r->c2r = &run_c2r;
+        c2r->c2c = &run_c2c; c2r->prepare_c2c = &prep_row_c2c; c2r->ppb_c2c = ppb_uw;
+        c2r->smem_c2c = (size_t)ppb_uw * smem_padded_len(rq.uw.n) * sizeof(float2);
+    }
+    if (!ok) { *err = "a JIT-compiled kernel was not found in the module"; jit_destroy(m); return false; }
+    *out_mod = m;
+    return true;
+}
+
+}  // namespace b2r

@@ -1,0 +1,31 @@
+// b2r_jit.h -- plan-time JIT (NVRTC) of statically scheduled kernels; see b2r_jit.cpp.
+#pragma once
+
+#include <string>
+
+#include "b2r_launch.h"
+
+namespace b2r {
+
+struct JitModule;   // one loaded module per plan (kernels are per CUDA context)
+
+struct JitRequest {
+    Schedule w, h, uh, uw;     // W (R2C rows), H / upH (columns, same thread count), upW (C2R rows)
+    bool want_r2c = false, want_cols = false, want_c2r = false;   // which kernels lack an ahead-of-time build
+    int precision = 0;         // 0 fp32, 2 fp16 storage
+    bool up2 = false;          // upW == 2*W: static first-stage operand pattern in the C2R kernel
+    bool c2c = false;          // also build k_c2c_rows (B2R_FLAG_C2C_PARITY)
+    int cc = 4;                // column tile width
+    int nx = 0;                // W/2 + 1
+    bool cache_only = false;   // only use a cubin already in the disk cache, never compile
+};
+
+// true when libcuda + libnvrtc could be loaded and B2R_JIT != 0
+bool jit_available(std::string* why);
+// Compiles (or fetches from the disk cache) and loads the requested kernels on the current device and
+// fills the launcher structs.  On failure returns false with a message; the caller falls back to the
+// dynamic kernels.
+bool jit_build(const JitRequest& rq, JitModule** out_mod, RowImpl* r2c, ColImpl* cols, RowImpl* c2r, std::string* err);
+void jit_destroy(JitModule* m);
+
+}  // namespace b2r

@@ -40,11 +40,13 @@ struct RowImpl {       // K1 or K7 resolved for one size
     Schedule sched;
     int ppb = 1;               // row pairs per CTA
     size_t smem = 0;
-    cudaError_t (*prepare)(size_t smem) = nullptr;   // per-device function attributes
-    cudaError_t (*r2c)(cudaStream_t, const R2cArgs&, int ppb, size_t smem) = nullptr;
-    cudaError_t (*c2r)(cudaStream_t, const C2rArgs&, int ppb, size_t smem) = nullptr;
-    cudaError_t (*c2c)(cudaStream_t, const C2rArgs&, int threads, size_t smem) = nullptr;   // k_c2c_rows, same schedule
-    cudaError_t (*prepare_c2c)(size_t smem) = nullptr;
+    const void* ctx = nullptr;  // launcher-private (JIT: the loaded kernels); passed back to every call below
+    bool is_jit = false;
+    cudaError_t (*prepare)(size_t smem, const void* ctx) = nullptr;   // per-device function attributes
+    cudaError_t (*r2c)(cudaStream_t, const R2cArgs&, int threads, size_t smem, const void* ctx) = nullptr;
+    cudaError_t (*c2r)(cudaStream_t, const C2rArgs&, int threads, size_t smem, const void* ctx) = nullptr;
+    cudaError_t (*c2c)(cudaStream_t, const C2rArgs&, int threads, size_t smem, const void* ctx) = nullptr;   // k_c2c_rows
+    cudaError_t (*prepare_c2c)(size_t smem, const void* ctx) = nullptr;
     int ppb_c2c = 1;
     size_t smem_c2c = 0;
 };
@@ -55,8 +57,10 @@ struct ColImpl {       // fused column kernel resolved for one (H, upH) pair
     Schedule fwd, inv;         // same thread count
     int cc = 4;                // spectrum columns per CTA
     size_t smem = 0;
-    cudaError_t (*prepare)(size_t smem) = nullptr;
-    cudaError_t (*launch)(cudaStream_t, const ColsArgs&, int threads, size_t smem) = nullptr;
+    const void* ctx = nullptr;
+    bool is_jit = false;
+    cudaError_t (*prepare)(size_t smem, const void* ctx) = nullptr;
+    cudaError_t (*launch)(cudaStream_t, const ColsArgs&, int threads, size_t smem, const void* ctx) = nullptr;
 };
 
 // static registries: return false when the size was not instantiated at build time

@@ -6,7 +6,7 @@ cudaError_t launch_sharpen_kernel(cudaStream_t s, const SharpenArgs& a) {
     const int bx = sharpen_rows_block(a.dm.up_w);
     if (bx > 0) {   // vectorised rolling-window kernel
         constexpr int RY = kSharpenRowsPerThread;
-        dim3 block(bx), grid(a.dm.up_w / 4 / bx, (a.dm.up_h + RY - 1) / RY, 3);
+        dim3 block(bx), grid((a.dm.up_w / 4 + bx - 1) / bx, (a.dm.up_h + RY - 1) / RY, 3);
         if (a.precision == 2)
             k_sharpen_rows<__half, RY><<<grid, block, 0, s>>>((const __half*)a.pre, (__half*)a.out, a.dm);
         else

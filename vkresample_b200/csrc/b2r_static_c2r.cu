@@ -6,7 +6,7 @@
 
 namespace b2r {
 namespace {
-template <class P, int PPB> cudaError_t prep(size_t smem) {
+template <class P, int PPB> cudaError_t prep(size_t smem, const void*) {
     if (smem <= 48 * 1024) return cudaSuccess;
     cudaError_t e;
     const int n = (int)smem;
@@ -15,7 +15,7 @@ template <class P, int PPB> cudaError_t prep(size_t smem) {
     if ((e = cudaFuncSetAttribute(k_c2r_rows<P, __half, PPB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, n))) return e;
     return cudaFuncSetAttribute(k_c2r_rows<P, __half, PPB, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, n);
 }
-template <class P, int PPB> cudaError_t run(cudaStream_t s, const C2rArgs& a, int, size_t smem) {
+template <class P, int PPB> cudaError_t run(cudaStream_t s, const C2rArgs& a, int, size_t smem, const void*) {
     const int pairs = 3 * a.dm.up_h / 2;
     dim3 block(P::kT, PPB), grid((pairs + PPB - 1) / PPB);
     const bool up2 = (a.dm.up_w == 2 * a.dm.w);   // exact 2x: first-stage operand pattern is static
@@ -32,7 +32,7 @@ template <class P, int PPB> cudaError_t run(cudaStream_t s, const C2rArgs& a, in
 // grid = resident CTAs of the device (see DESIGN.md section 4 for the measured comparison with the
 // direct-load kernel).
 constexpr size_t kBulkSmemMax = 16 + 4 * 4100 * sizeof(float2);   // staging for nx <= 4100 (W <= 8198)
-template <class P> cudaError_t prep_bulk(size_t) {
+template <class P> cudaError_t prep_bulk(size_t, const void*) {
     const int n = (int)(kBulkSmemMax + smem_padded_len(P::kN) * sizeof(float2));
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(k_c2r_rows_bulk<P, float, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, n))) return e;
@@ -55,20 +55,20 @@ template <class P, class TOut, bool UP2> cudaError_t run_bulk_t(cudaStream_t s, 
     k_c2r_rows_bulk<P, TOut, UP2><<<grid, P::kT, smem, s>>>(a.spec, (TOut*)a.pre, a.tw, P{}, a.dm, pairs, a.scale);
     return cudaGetLastError();
 }
-template <class P, int PPB> cudaError_t run_bulk(cudaStream_t s, const C2rArgs& a, int, size_t) {
+template <class P, int PPB> cudaError_t run_bulk(cudaStream_t s, const C2rArgs& a, int, size_t, const void*) {
     const bool up2 = (a.dm.up_w == 2 * a.dm.w);
     if (a.precision == 2) return up2 ? run_bulk_t<P, __half, true>(s, a) : run_bulk_t<P, __half, false>(s, a);
     return up2 ? run_bulk_t<P, float, true>(s, a) : run_bulk_t<P, float, false>(s, a);
 }
 
 // ---- C2C parity mode rows (k_c2c_rows): same schedule, one complex transform per output row
-template <class P, int PPB> cudaError_t prep_c2c(size_t smem) {
+template <class P, int PPB> cudaError_t prep_c2c(size_t smem, const void*) {
     if (smem <= 48 * 1024) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(k_c2c_rows<P, float, PPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_c2c_rows<P, __half, PPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
-template <class P, int PPB> cudaError_t run_c2c(cudaStream_t s, const C2rArgs& a, int, size_t smem) {
+template <class P, int PPB> cudaError_t run_c2c(cudaStream_t s, const C2rArgs& a, int, size_t smem, const void*) {
     const int rows = 3 * a.dm.up_h;
     dim3 block(P::kT, PPB), grid((rows + PPB - 1) / PPB);
     if (a.precision == 2)

@@ -7,11 +7,11 @@
 
 namespace b2r {
 namespace {
-template <class PF, class PI, int CC> cudaError_t prep(size_t smem) {
+template <class PF, class PI, int CC> cudaError_t prep(size_t smem, const void*) {
     if (smem <= 48 * 1024) return cudaSuccess;
     return cudaFuncSetAttribute(k_cols<PF, PI, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
-template <class PF, class PI, int CC> cudaError_t run(cudaStream_t s, const ColsArgs& a, int, size_t smem) {
+template <class PF, class PI, int CC> cudaError_t run(cudaStream_t s, const ColsArgs& a, int, size_t smem, const void*) {
     dim3 block(PI::kT * CC), grid((a.dm.nx + CC - 1) / CC, 3);
     k_cols<PF, PI, CC><<<grid, block, smem, s>>>(a.in, a.out, a.tw_f, a.tw_i, PF{}, PI{}, a.dm, a.scale, a.nyq);
     return cudaGetLastError();
@@ -19,7 +19,7 @@ template <class PF, class PI, int CC> cudaError_t run(cudaStream_t s, const Cols
 template <class PF, class PI, int CC> constexpr bool grouped_ok() {
     return PI::kT % 32 == 0 && PF::kStages >= 2 && PI::kStages >= 3 && CC <= 15;
 }
-template <class PF, class PI, int CC> cudaError_t prep_grouped(size_t smem) {
+template <class PF, class PI, int CC> cudaError_t prep_grouped(size_t smem, const void*) {
     if constexpr (grouped_ok<PF, PI, CC>()) {
         if (smem <= 48 * 1024) return cudaSuccess;
         return cudaFuncSetAttribute(k_cols_grouped<PF, PI, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -27,7 +27,7 @@ template <class PF, class PI, int CC> cudaError_t prep_grouped(size_t smem) {
         return cudaErrorInvalidValue;
     }
 }
-template <class PF, class PI, int CC> cudaError_t run_grouped(cudaStream_t s, const ColsArgs& a, int, size_t smem) {
+template <class PF, class PI, int CC> cudaError_t run_grouped(cudaStream_t s, const ColsArgs& a, int, size_t smem, const void*) {
     if constexpr (grouped_ok<PF, PI, CC>()) {
         dim3 block(PI::kT * CC), grid((a.dm.nx + CC - 1) / CC, 3);
         k_cols_grouped<PF, PI, CC><<<grid, block, smem, s>>>(a.in, a.out, a.tw_f, a.tw_i, PF{}, PI{}, a.dm, a.scale, a.nyq);

@@ -4,13 +4,13 @@
 
 namespace b2r {
 namespace {
-template <class P, int PPB> cudaError_t prep(size_t smem) {
+template <class P, int PPB> cudaError_t prep(size_t smem, const void*) {
     if (smem <= 48 * 1024) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(k_r2c_rows<P, float, PPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(k_r2c_rows<P, __half, PPB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
 }
-template <class P, int PPB> cudaError_t run(cudaStream_t s, const R2cArgs& a, int, size_t smem) {
+template <class P, int PPB> cudaError_t run(cudaStream_t s, const R2cArgs& a, int, size_t smem, const void*) {
     const int pairs = 3 * a.dm.h / 2;
     dim3 block(P::kT, PPB), grid((pairs + PPB - 1) / PPB);
     if (a.precision == 2)
