@@ -79,7 +79,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._pump, daemon=True)
             self.t.start()
@@ -88,9 +88,11 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.perf_counter(), [c.strip() for c in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t0=None, t1=None):
+        """summary of the samples taken inside [t0, t1] (the timed region); if the region was too short
+        to catch one, of all samples since start() (warm-up + timed region, same load) -- `window` says which"""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -101,7 +103,9 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        inside = [r for (t, r) in self.rows if t0 is not None and t0 <= t <= t1 + 0.02]
+        window = "timed region" if inside else "warm-up + timed region"
+        for r in (inside if inside else [r for (_, r) in self.rows]):
             try:
                 sm.append(float(r[0])); mx.append(float(r[1]))
                 for n, v in zip(names, r[3:7]):
@@ -110,7 +114,7 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "window": window, "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------------------ CPU arms
@@ -209,21 +213,23 @@ def run_b200(args):
             k = (i0 + f) % ring
             plan.enqueue_device(d_in[k].data_ptr(), d_out[k].data_ptr())
 
+    sampler = ClockSampler(local)
+    sampler.start()                  # runs through warm-up and the timed region; summarised per window below
+    time.sleep(0.05)
     for i in range(args.warmup):
         step(i * F)
     plan.synchronize()
 
-    sampler = ClockSampler(local)
     launches0 = plan.launch_count
     barrier()
-    sampler.start()
     t_wall0 = time.perf_counter()
     plan.timer_start()
     for i in range(args.steps):
         step(i * F)
     ms = plan.timer_stop()          # CUDA events on the launching stream
-    t_wall = time.perf_counter() - t_wall0
-    clocks = sampler.stop()
+    t_wall1 = time.perf_counter()
+    t_wall = t_wall1 - t_wall0
+    clocks = sampler.stop(t_wall0, t_wall1)
     barrier()
     launches = plan.launch_count - launches0
 
