@@ -18,7 +18,7 @@
  *   - there is NO CPU fallback: without a CUDA device every compute entry point fails with
  *     B2R_ERR_CUDA.
  *
- * Data layouts (elements are float for precision 0, IEEE binary16 for precision 2):
+ * Data layouts (elements are float for precision 0, double for precision 1, IEEE binary16 for precision 2):
  *   input   planar [3][H][W], row stride W, plane stride (W+2)*H elements -- exactly the buffer
  *           launchResample fills at VkResample.cpp:1636-1685 (2*H unused pad elements per plane).
  *           Size = b2r_plan_input_bytes() = 3 * elem * (W+2) * H  (== 3*complexSize*(W/2+1)*H, :1437).
@@ -38,10 +38,11 @@ extern "C" {
 #define B2R_SUCCESS 0
 #define B2R_ERR_INVALID_ARG (-1)   /* bad size / factor / precision / null pointer            */
 #define B2R_ERR_CUDA (-2)          /* CUDA runtime error or no device (message has the detail) */
-#define B2R_ERR_UNSUPPORTED (-3)   /* e.g. precision 1 (double), size not 2^a 3^b 5^c 7^d      */
+#define B2R_ERR_UNSUPPORTED (-3)   /* e.g. size not 2^a 3^b 5^c 7^d, precision 1 without NVRTC  */
 #define B2R_ERR_NOMEM (-4)
 
 #define B2R_PRECISION_FP32 0u      /* -p 0, VkResample.cpp:1860-1866 */
+#define B2R_PRECISION_FP64 1u      /* -p 1: double storage and arithmetic; kernels compiled at plan time */
 #define B2R_PRECISION_FP16 2u      /* -p 2: half storage, fp32 FFT arithmetic, half sharpen     */
 
 /* flags for b2r_plan_create */
@@ -90,7 +91,7 @@ int b2r_device_name(int device, char* buf, size_t buf_len);
 
 /* Plan build.  Replaces the configuration fill + allocateFFTBuffer x3 (VkResample.cpp:1409-1448),
  * initializeVulkanFFT x2 (:1506-1509), createShiftApp (:1562) and createSharpenApp (:1617).
- * upscale: float, upW = (uint32)(upscale*W) as in the reference.  precision: 0 or 2. */
+ * upscale: float, upW = (uint32)(upscale*W) as in the reference.  precision: 0, 1 or 2 (1 needs NVRTC). */
 int b2r_plan_create(b2r_plan** out, int device, uint32_t w, uint32_t h, float upscale,
                     uint32_t precision, float sharpen, uint32_t flags);
 /* deleteVulkanFFT x2, deleteShiftApp x2, vkDestroyBuffer/vkFreeMemory, VkResample.cpp:1762-1778 */

@@ -111,6 +111,8 @@ def fill_input(u8_hwc: np.ndarray, precision: int = 0) -> np.ndarray:
     x = np.ascontiguousarray(np.moveaxis(x, -1, 0))
     if precision == 2:
         return x.astype(np.float16)
+    if precision == 1:
+        return x                      # (double)u8 / 255.0, VkResample.cpp:1659
     return x.astype(np.float32)
 
 
@@ -176,13 +178,13 @@ def inverse_plane(b: np.ndarray, plan: FramePlan, workers=None) -> np.ndarray:
 def store_pre_sharpen(o: np.ndarray, precision: int) -> np.ndarray:
     """C2R store type: float, or float16_t round-to-nearest in half-memory mode
     (vkFFT.h:3525-3527, :7280-7293)."""
-    return o.astype(np.float16 if precision == 2 else np.float32)
+    return o.astype({0: np.float32, 1: np.float64, 2: np.float16}[precision])
 
 
 def pre_sharpen(x: np.ndarray, plan: FramePlan, precision: int = 0, dtype=np.float64,
                 workers=None) -> np.ndarray:
     """a3..a7: planar input -> stored C2R plane [3, upH, upW] (= interp / up^2)."""
-    f = forward_spectrum(np.asarray(x, dtype=np.float32 if dtype == np.float32 else np.float64),
+    f = forward_spectrum(np.asarray(x, dtype=np.float32 if (dtype == np.float32 and precision != 1) else np.float64),
                          dtype=dtype, workers=workers)
     o = inverse_plane(shift_zero_pad(f, plan), plan, workers=workers)
     return store_pre_sharpen(o, precision)
@@ -254,15 +256,17 @@ def sharpen(pre: np.ndarray, plan: FramePlan, sharpen_const: float = 0.2,
     threads (identical results; used by the timed CPU baseline).
     """
     if dtype is None:
-        dtype = np.float16 if precision == 2 else np.float32
+        dtype = {0: np.float32, 1: np.float64, 2: np.float16}[precision]
     dt = np.dtype(dtype).type
     up_w, up_h, ps = plan.up_w, plan.up_h, plan.pre_plane_stride
     flat = _flat_with_pad(pre, plan).astype(dtype)
+    # the "%f" texts are float literals in the fp32 / fp16 shaders and double literals in the -p 1 shader
+    lit = (lambda v: float("%f" % float(np.float32(v)))) if precision == 1 else _literal
     # tex = up2 * in ; len = |tex| clamped to [0,1]     (:893-907)
-    t_all = np.abs(dt(_literal(plan.up2)) * flat)
+    t_all = np.abs(dt(lit(plan.up2)) * flat)
     t_all = np.minimum(t_all, dt(1.0))
     t_all = np.maximum(t_all, dt(0.0))
-    s = dt(_literal(sharpen_const))
+    s = dt(lit(sharpen_const))
     out = np.empty((pre.shape[0], up_h, up_w), dtype=dtype)
     nw = int(workers) if workers else 1
     jobs = []
@@ -315,7 +319,7 @@ def upscale_frame(x: np.ndarray, upscale: float = 2.0, sharpen_const: float = 0.
     out = sharpen(pre, plan, sharpen_const, precision, dtype=sh_dtype, workers=workers)
     if precision == 2 and dtype != np.float64:
         out = out.astype(np.float16)
-    elif dtype != np.float64:
+    elif dtype != np.float64 and precision != 1:
         out = out.astype(np.float32)
     if return_pre:
         return out, pre

@@ -35,9 +35,8 @@ def test_no_torch_types_in_header():
 def test_invalid_arguments_fail_loudly():
     lib = _lib_or_skip()
     h = ctypes.c_void_p()
-    # precision 1 (double) is unsupported, like -p 1 without the future double path
-    assert lib.b2r_plan_create(ctypes.byref(h), 0, 256, 128, 2.0, 1, 0.2, 0) == -3
-    assert b"double" in lib.b2r_last_error()
+    assert lib.b2r_plan_create(ctypes.byref(h), 0, 256, 128, 2.0, 3, 0.2, 0) == -1   # precision must be 0 / 1 / 2
+    assert b"precision" in lib.b2r_last_error()
     assert lib.b2r_plan_create(ctypes.byref(h), 0, 255, 128, 2.0, 0, 0.2, 0) == -1   # odd width
     assert lib.b2r_plan_create(ctypes.byref(h), 0, 256, 128, 0.5, 0, 0.2, 0) == -1   # factor < 1
     assert lib.b2r_plan_create(ctypes.byref(h), 0, 2 * 11, 128, 2.0, 0, 0.2, 0) == -3  # prime factor 11

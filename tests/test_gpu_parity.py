@@ -338,3 +338,37 @@ def test_plan_time_jit(w, h, up, prec, tmp_path, monkeypatch):
         out = p1.upscale(vo.synthetic_frame("noise", w, h).astype(p1.dtype))
     tol = 2e-4 if prec == 0 else 1e-2
     assert np.abs(out.astype(np.float64) - ref.astype(np.float64)).max() <= tol
+
+
+@pytest.mark.parametrize("w,h,up", [(256, 128, 2.0), (2048, 1024, 2.0), (600, 360, 1.5), (1920, 1080, 2.0)])
+def test_double_precision(w, h, up):
+    """-p 1 (VkResample.cpp:1860-1866): double storage and arithmetic.  The whole kernel set is compiled
+    at plan time with -DB2R_REAL_IS_DOUBLE; compared with the float64 oracle (double literals in the
+    sharpen, like the dvec2/double shader the reference generates)."""
+    plan_o = vo.make_plan(w, h, up)
+    x = vo.synthetic_frame("noise", w, h).astype(np.float64)
+    with vb.Plan(w, h, up, 1, 0.2) as p:
+        assert p.dtype == np.float64 and p.info.jit_kernels == 7
+        assert p.output_bytes == 3 * 8 * p.up_w * p.up_h
+        out = p.upscale(x)
+        pre = p.download_pre_sharpen()
+        ms = p.execute(3)
+    pre_o = vo.pre_sharpen(x, plan_o, precision=1, dtype=np.float64, workers=WORKERS)
+    e_pre = np.abs(pre - pre_o).max() * plan_o.up2
+    sh_o = vo.sharpen(pre, plan_o, 0.2, 1)
+    same = bool(np.all((sh_o.view(np.uint64) == out.view(np.uint64)) | (np.isnan(sh_o) & np.isnan(out))))
+    o64 = vo.upscale_frame(x, up, 0.2, 1, dtype=np.float64, workers=WORKERS)
+    e2e = np.abs(out - o64).max()
+    print(f"\n[fp64] {w}x{h} x{up}: pre*up2 max-abs {e_pre:.3e}  sharpen bit-exact {same}  e2e max-abs {e2e:.3e}  {ms*1e3:.0f} us/frame")
+    assert e_pre <= 1e-13 and same and e2e <= 1e-9
+
+
+def test_double_precision_u8_api():
+    rng = np.random.default_rng(4)
+    img = rng.integers(0, 256, (120, 160, 3), dtype=np.uint8)
+    with vb.Plan(160, 120, 2.0, 1, 0.2) as p:
+        got = p.upscale_u8(img)
+    ref = vo.upscale_u8(img, 2.0, 0.2, 1, dtype=np.float64)
+    d = np.abs(got.astype(np.int16) - ref.astype(np.int16))
+    d = np.minimum(d, 256 - d)
+    assert d.max() <= 1 and (d == 0).mean() > 0.9999

@@ -20,6 +20,7 @@ __all__ = ["Plan", "B2RError", "library_path", "load_library", "device_count", "
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 PRECISION_FP32 = 0
+PRECISION_FP64 = 1
 PRECISION_FP16 = 2
 FLAG_NO_GRAPH = 1
 FLAG_NO_SHARPEN_LITERAL_ROUNDING = 2
@@ -155,7 +156,7 @@ class Plan:
         self.info = info
         self.w, self.h, self.up_w, self.up_h = info.w, info.h, info.up_w, info.up_h
         self.precision = info.precision
-        self.dtype = np.float16 if info.precision == 2 else np.float32
+        self.dtype = {0: np.float32, 1: np.float64, 2: np.float16}[int(info.precision)]
         self.input_bytes, self.output_bytes = info.input_bytes, info.output_bytes
         self.device = device
 

@@ -49,6 +49,11 @@ float literal_f(float v) {  // value of the "%f" text the reference pastes into 
     snprintf(t, sizeof t, "%f", (double)v);
     return strtof(t, nullptr);
 }
+double literal_d(float v) {  // the same text read as a double literal (-p 1 shader)
+    char t[64];
+    snprintf(t, sizeof t, "%f", (double)v);
+    return strtod(t, nullptr);
+}
 int env_int(const char* name, int dflt) {
     const char* s = getenv(name);
     return (s && *s) ? atoi(s) : dflt;
@@ -114,7 +119,8 @@ namespace {
 
 int launch_sharpen(b2r_plan* p, cudaStream_t s, void* d_out = nullptr, const Lane* ln = nullptr) {
     SharpenArgs a{ln ? ln->d_pre : p->d_pre, d_out ? d_out : (ln ? ln->d_out : p->d_out), p->dm, p->g.precision};
-    CU(launch_sharpen_kernel(s, a));
+    if (p->g.precision == 1) CU(jit_launch_sharpen(p->jit, s, a));
+    else CU(launch_sharpen_kernel(s, a));
     return B2R_SUCCESS;
 }
 
@@ -166,13 +172,21 @@ int build(b2r_plan* p) {
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, p->device));
     const size_t smem_max = prop.sharedMemPerBlockOptin;
-    const bool force_dyn = env_int("B2R_FORCE_DYNAMIC", 0) != 0;
+    const bool dbl = g.precision == 1;
+    // fp64: nothing is built ahead of time -- the whole kernel set is compiled at plan time; the static
+    // table still supplies the schedule for the sizes it lists
+    const bool force_dyn = env_int("B2R_FORCE_DYNAMIC", 0) != 0 || dbl;
+    const size_t cb = g.cplx_bytes();
+    RowImpl st_r2c, st_c2r; ColImpl st_cols;
+    const bool has_r2c = find_static_r2c(g.w, &st_r2c), has_c2r = find_static_c2r(g.up_w, &st_c2r);
+    const bool has_cols = find_static_cols(g.h, g.up_h, &st_cols);
 
     // ---- resolve kernels: static schedule when the size was instantiated, else dynamic
     if (!force_dyn && find_static_r2c(g.w, &p->k_r2c)) {
         build_fft(g.w, p->k_r2c.sched.radices, p->k_r2c.sched.nst, p->k_r2c.sched.threads, &p->fw);
     } else {
-        if (!schedule_fft(g.w, &p->fw, &err)) return fail(B2R_ERR_UNSUPPORTED, "%s", err.c_str());
+        if (dbl && has_r2c) build_fft(g.w, st_r2c.sched.radices, st_r2c.sched.nst, st_r2c.sched.threads, &p->fw);
+        else if (!schedule_fft(g.w, &p->fw, &err)) return fail(B2R_ERR_UNSUPPORTED, "%s", err.c_str());
         get_dynamic_r2c(&p->k_r2c);
         sched_from(p->fw, &p->k_r2c.sched);
         p->k_r2c.smem = (size_t)p->k_r2c.ppb * smem_padded_len(g.w) * sizeof(float2);
@@ -180,7 +194,8 @@ int build(b2r_plan* p) {
     if (!force_dyn && find_static_c2r(g.up_w, &p->k_c2r)) {
         build_fft(g.up_w, p->k_c2r.sched.radices, p->k_c2r.sched.nst, p->k_c2r.sched.threads, &p->fuw);
     } else {
-        if (!schedule_fft(g.up_w, &p->fuw, &err)) return fail(B2R_ERR_UNSUPPORTED, "%s", err.c_str());
+        if (dbl && has_c2r) build_fft(g.up_w, st_c2r.sched.radices, st_c2r.sched.nst, st_c2r.sched.threads, &p->fuw);
+        else if (!schedule_fft(g.up_w, &p->fuw, &err)) return fail(B2R_ERR_UNSUPPORTED, "%s", err.c_str());
         get_dynamic_c2r(&p->k_c2r);
         sched_from(p->fuw, &p->k_c2r.sched);
         p->k_c2r.smem = (size_t)p->k_c2r.ppb * smem_padded_len(g.up_w) * sizeof(float2);
@@ -189,11 +204,17 @@ int build(b2r_plan* p) {
         build_fft(g.h, p->k_cols.fwd.radices, p->k_cols.fwd.nst, p->k_cols.fwd.threads, &p->fh);
         build_fft(g.up_h, p->k_cols.inv.radices, p->k_cols.inv.nst, p->k_cols.inv.threads, &p->fuh);
     } else {
-        if (!schedule_fft(g.h, &p->fh, &err) || !schedule_fft(g.up_h, &p->fuh, &err))
-            return fail(B2R_ERR_UNSUPPORTED, "%s", err.c_str());
-        const int tc = std::max(p->fh.desc.threads, p->fuh.desc.threads);
-        schedule_fft(g.h, &p->fh, &err, tc);
-        schedule_fft(g.up_h, &p->fuh, &err, tc);
+        if (dbl && has_cols) {
+            build_fft(g.h, st_cols.fwd.radices, st_cols.fwd.nst, st_cols.fwd.threads, &p->fh);
+            build_fft(g.up_h, st_cols.inv.radices, st_cols.inv.nst, st_cols.inv.threads, &p->fuh);
+        } else {
+            if (!schedule_fft(g.h, &p->fh, &err) || !schedule_fft(g.up_h, &p->fuh, &err))
+                return fail(B2R_ERR_UNSUPPORTED, "%s", err.c_str());
+            const int tc0 = std::max(p->fh.desc.threads, p->fuh.desc.threads);
+            schedule_fft(g.h, &p->fh, &err, tc0);
+            schedule_fft(g.up_h, &p->fuh, &err, tc0);
+        }
+        const int tc = p->fuh.desc.threads;
         // column tile: widest of {8,4,2} with <= 512 threads and room for >= 2 CTAs per SM
         int cc = env_int("B2R_COLS_CC", 0);
         if (cc != 1 && cc != 2 && cc != 4 && cc != 8) {
@@ -207,7 +228,7 @@ int build(b2r_plan* p) {
         p->k_cols.smem = (size_t)smem_padded_len(g.up_h * p->k_cols.cc) * sizeof(float2);
     }
     // ---- plan-time JIT for whatever has no ahead-of-time schedule (the reference JIT-compiles every plan)
-    if (!force_dyn && !(p->flags & B2R_FLAG_NO_JIT) &&
+    if ((dbl || (!force_dyn && !(p->flags & B2R_FLAG_NO_JIT))) &&
         (!p->k_r2c.is_static || !p->k_cols.is_static || !p->k_c2r.is_static)) {
         std::string why;
         if (jit_available(&why)) {
@@ -216,8 +237,10 @@ int build(b2r_plan* p) {
             rq.want_r2c = !p->k_r2c.is_static; rq.want_cols = !p->k_cols.is_static; rq.want_c2r = !p->k_c2r.is_static;
             rq.precision = g.precision; rq.up2 = (g.up_w == 2 * g.w); rq.c2c = p->c2c; rq.nx = g.nx;
             rq.cache_only = false;
+            rq.want_pixels = dbl; rq.up_w = g.up_w;
             const int tc = rq.uh.threads;
-            rq.cc = (tc <= 32) ? 8 : ((4 * tc <= 1024 && smem_padded_len(g.up_h * 4) * sizeof(float2) <= 110 * 1024) ? 4 : 2);
+            rq.cc = (tc <= 32) ? 8 : ((4 * tc <= 1024 && smem_padded_len(g.up_h * 4) * cb <= (dbl ? 200u : 110u) * 1024) ? 4 : 2);
+            if (dbl && has_cols && (size_t)smem_padded_len(g.up_h * st_cols.cc) * cb <= smem_max) rq.cc = st_cols.cc;
             RowImpl jr, jc; ColImpl jcol;
             if (jit_build(rq, &p->jit, &jr, &jcol, &jc, &why)) {
                 if (rq.want_r2c) p->k_r2c = jr;
@@ -230,6 +253,8 @@ int build(b2r_plan* p) {
             p->jit_note = why;
         }
     }
+    if (dbl && !(p->k_r2c.is_jit && p->k_cols.is_jit && p->k_c2r.is_jit))
+        return fail(B2R_ERR_UNSUPPORTED, "precision 1 (double) needs the plan-time JIT: %s", p->jit_note.c_str());
     const int lim_c = p->k_cols.is_static ? 1024 : kDynMaxThreads;
     const int lim_1 = p->k_r2c.is_static ? 1024 : kDynMaxThreads, lim_7 = p->k_c2r.is_static ? 1024 : kDynMaxThreads;
     if (p->k_cols.cc * p->k_cols.inv.threads > lim_c || p->k_cols.smem > smem_max)
@@ -241,7 +266,7 @@ int build(b2r_plan* p) {
     CU(p->k_r2c.prepare(p->k_r2c.smem, p->k_r2c.ctx));
     CU(p->k_c2r.prepare(p->k_c2r.smem, p->k_c2r.ctx));
     if (p->c2c) {
-        if (!p->k_c2r.is_static) p->k_c2r.smem_c2c = (size_t)p->k_c2r.ppb_c2c * smem_padded_len(g.up_w) * sizeof(float2);
+        if (!p->k_c2r.is_static) p->k_c2r.smem_c2c = (size_t)p->k_c2r.ppb_c2c * smem_padded_len(g.up_w) * cb;
         if (p->k_c2r.sched.threads * p->k_c2r.ppb_c2c > lim_7 || p->k_c2r.smem_c2c > smem_max)
             return fail(B2R_ERR_UNSUPPORTED, "row transform %d does not fit one CTA", g.up_w);
         CU(p->k_c2r.prepare_c2c(p->k_c2r.smem_c2c, p->k_c2r.ctx));
@@ -256,24 +281,26 @@ int build(b2r_plan* p) {
     const bool raw = p->flags & B2R_FLAG_NO_SHARPEN_LITERAL_ROUNDING;
     d.up2 = raw ? g.up2 : literal_f(g.up2);
     d.sharpen = raw ? g.sharpen : literal_f(g.sharpen);
+    d.up2_d = raw ? (double)g.up2 : literal_d(g.up2);
+    d.sharpen_d = raw ? (double)g.sharpen : literal_d(g.sharpen);
 
     // device memory
     const size_t eb = g.elem_bytes();
     const size_t b_in = g.input_bytes(), b_pre = g.pre_elems * eb, b_out = g.output_bytes();
-    const size_t b_s1 = g.spec_in_elems() * sizeof(float2), b_s2 = g.spec_out_elems() * sizeof(float2);
+    const size_t b_s1 = g.spec_in_elems() * cb, b_s2 = g.spec_out_elems() * cb;
     const size_t n_tw = p->fw.twiddles.size() + p->fh.twiddles.size() + p->fuh.twiddles.size() + p->fuw.twiddles.size();
     CU(cudaMalloc(&p->d_in, b_in));
     CU(cudaMalloc(&p->d_pre, b_pre));
     CU(cudaMalloc(&p->d_out, b_out));
     CU(cudaMalloc((void**)&p->d_spec1, b_s1));
     CU(cudaMalloc((void**)&p->d_spec2, b_s2));
-    CU(cudaMalloc((void**)&p->d_tw, (n_tw + 1) * sizeof(float2)));
+    CU(cudaMalloc((void**)&p->d_tw, (n_tw + 1) * cb));
     CU(cudaMalloc((void**)&p->d_fd, 4 * sizeof(FftDesc)));
     if (p->c2c) {
-        CU(cudaMalloc((void**)&p->d_nyq, 3 * (size_t)g.spec_stride * sizeof(float2)));
-        CU(cudaMemset(p->d_nyq, 0, 3 * (size_t)g.spec_stride * sizeof(float2)));
+        CU(cudaMalloc((void**)&p->d_nyq, 3 * (size_t)g.spec_stride * cb));
+        CU(cudaMemset(p->d_nyq, 0, 3 * (size_t)g.spec_stride * cb));
     }
-    p->device_bytes = b_in + b_pre + b_out + b_s1 + b_s2 + (n_tw + 1) * sizeof(float2) + 4 * sizeof(FftDesc);
+    p->device_bytes = b_in + b_pre + b_out + b_s1 + b_s2 + (n_tw + 1) * cb + 4 * sizeof(FftDesc);
     CU(cudaMemset(p->d_in, 0, b_in));
     CU(cudaMemset(p->d_pre, 0, b_pre));  // the plane pad regions stay zero for the plan's lifetime
     CU(cudaMemset(p->d_spec1, 0, b_s1));
@@ -281,10 +308,13 @@ int build(b2r_plan* p) {
     const FftDesc descs[4] = {p->fw.desc, p->fh.desc, p->fuh.desc, p->fuw.desc};
     CU(cudaMemcpy(p->d_fd, descs, sizeof descs, cudaMemcpyHostToDevice));
     size_t off = 0;
-    auto put = [&](const HostFft& f, const float2** slot) -> int {
-        *slot = p->d_tw + off;
-        if (!f.twiddles.empty())
-            CU(cudaMemcpy(p->d_tw + off, f.twiddles.data(), f.twiddles.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    auto put = [&](const HostFft& f, const float2** slot) -> int {   // fp64: the table holds double2 (byte offsets scale with cb)
+        char* base = reinterpret_cast<char*>(p->d_tw) + off * cb;
+        *slot = reinterpret_cast<const float2*>(base);
+        if (!f.twiddles.empty()) {
+            if (dbl) CU(cudaMemcpy(base, f.twiddles_d.data(), f.twiddles_d.size() * sizeof(double2), cudaMemcpyHostToDevice));
+            else CU(cudaMemcpy(base, f.twiddles.data(), f.twiddles.size() * sizeof(float2), cudaMemcpyHostToDevice));
+        }
         off += f.twiddles.size();
         return B2R_SUCCESS;
     };
@@ -335,7 +365,6 @@ int b2r_plan_create(b2r_plan** out, int device, uint32_t w, uint32_t h, float up
                     float sharpen, uint32_t flags) {
     if (!out) return fail(B2R_ERR_INVALID_ARG, "out is null");
     *out = nullptr;
-    if (precision == 1) return fail(B2R_ERR_UNSUPPORTED, "precision 1 (double) is not supported; use 0 (fp32) or 2 (fp16)");
     Geometry g;
     std::string err;
     const bool c2c = (flags & B2R_FLAG_C2C_PARITY) != 0;
@@ -502,18 +531,19 @@ int b2r_plan_set_lanes(b2r_plan* p, uint32_t lanes) {
         CU(cudaMalloc(&l.d_in, g.input_bytes()));
         CU(cudaMalloc(&l.d_pre, g.pre_elems * eb));
         CU(cudaMalloc(&l.d_out, g.output_bytes()));
-        CU(cudaMalloc((void**)&l.d_spec1, g.spec_in_elems() * sizeof(float2)));
-        CU(cudaMalloc((void**)&l.d_spec2, g.spec_out_elems() * sizeof(float2)));
+        const size_t cb = g.cplx_bytes();
+        CU(cudaMalloc((void**)&l.d_spec1, g.spec_in_elems() * cb));
+        CU(cudaMalloc((void**)&l.d_spec2, g.spec_out_elems() * cb));
         CU(cudaMemset(l.d_in, 0, g.input_bytes()));
         CU(cudaMemset(l.d_pre, 0, g.pre_elems * eb));
-        CU(cudaMemset(l.d_spec1, 0, g.spec_in_elems() * sizeof(float2)));
-        CU(cudaMemset(l.d_spec2, 0, g.spec_out_elems() * sizeof(float2)));
+        CU(cudaMemset(l.d_spec1, 0, g.spec_in_elems() * cb));
+        CU(cudaMemset(l.d_spec2, 0, g.spec_out_elems() * cb));
         if (p->c2c) {
-            CU(cudaMalloc((void**)&l.d_nyq, 3 * (size_t)g.spec_stride * sizeof(float2)));
-            CU(cudaMemset(l.d_nyq, 0, 3 * (size_t)g.spec_stride * sizeof(float2)));
+            CU(cudaMalloc((void**)&l.d_nyq, 3 * (size_t)g.spec_stride * cb));
+            CU(cudaMemset(l.d_nyq, 0, 3 * (size_t)g.spec_stride * cb));
         }
         p->device_bytes += g.input_bytes() + g.pre_elems * eb + g.output_bytes() +
-                           (g.spec_in_elems() + g.spec_out_elems()) * sizeof(float2);
+                           (g.spec_in_elems() + g.spec_out_elems()) * cb;
         p->extra.push_back(l);
     }
     CU(cudaDeviceSynchronize());
@@ -570,7 +600,8 @@ int b2r_upload_u8(b2r_plan* p, const unsigned char* host_hwc) {
     int rc = u8_buffers(p, 0, &in, &out);
     if (rc) return rc;
     CU(cudaMemcpyAsync(in, host_hwc, b2r_plan_input_u8_bytes(p), cudaMemcpyHostToDevice, p->stream));
-    CU(launch_u8_to_planar(p->stream, in, p->d_in, p->dm, p->g.precision));
+    if (p->g.precision == 1) CU(jit_launch_u8_to_planar(p->jit, p->stream, in, p->d_in, p->dm));
+    else CU(launch_u8_to_planar(p->stream, in, p->d_in, p->dm, p->g.precision));
     p->launches += 1;
     CU(cudaStreamSynchronize(p->stream));
     return B2R_SUCCESS;
@@ -582,7 +613,8 @@ int b2r_download_u8(b2r_plan* p, unsigned char* host_hwc) {
     unsigned char *in, *out;
     int rc = u8_buffers(p, 0, &in, &out);
     if (rc) return rc;
-    CU(launch_planar_to_u8(p->stream, p->d_out, out, p->dm, p->g.precision));
+    if (p->g.precision == 1) CU(jit_launch_planar_to_u8(p->jit, p->stream, p->d_out, out, p->dm));
+    else CU(launch_planar_to_u8(p->stream, p->d_out, out, p->dm, p->g.precision));
     p->launches += 1;
     CU(cudaMemcpyAsync(host_hwc, out, b2r_plan_output_u8_bytes(p), cudaMemcpyDeviceToHost, p->stream));
     CU(cudaStreamSynchronize(p->stream));
@@ -598,10 +630,12 @@ int b2r_enqueue_host_u8(b2r_plan* p, const unsigned char* host_in, unsigned char
     int rc = u8_buffers(p, li, &in, &out);
     if (rc) return rc;
     CU(cudaMemcpyAsync(in, host_in, b2r_plan_input_u8_bytes(p), cudaMemcpyHostToDevice, l.stream));
-    CU(launch_u8_to_planar(l.stream, in, l.d_in, p->dm, p->g.precision));
+    if (p->g.precision == 1) CU(jit_launch_u8_to_planar(p->jit, l.stream, in, l.d_in, p->dm));
+    else CU(launch_u8_to_planar(l.stream, in, l.d_in, p->dm, p->g.precision));
     rc = launch_frame(p, l.stream, l.d_in, l.d_out, nullptr, li ? &l : nullptr);
     if (rc) return rc;
-    CU(launch_planar_to_u8(l.stream, l.d_out, out, p->dm, p->g.precision));
+    if (p->g.precision == 1) CU(jit_launch_planar_to_u8(p->jit, l.stream, l.d_out, out, p->dm));
+    else CU(launch_planar_to_u8(l.stream, l.d_out, out, p->dm, p->g.precision));
     p->launches += p->kernels_per_frame + 2;
     CU(cudaMemcpyAsync(host_out, out, b2r_plan_output_u8_bytes(p), cudaMemcpyDeviceToHost, l.stream));
     return B2R_SUCCESS;

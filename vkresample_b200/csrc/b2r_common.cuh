@@ -108,3 +108,28 @@ __device__ __forceinline__ void b2r_mbar_wait(unsigned long long* bar, unsigned 
     } while (!done);
 }
 #endif
+
+// ---- arithmetic type of the FFT pipeline ---------------------------------------------------------
+// float for -p 0 / -p 2 (half is a storage type only, vkFFT.h:7280-7293); the whole header set is
+// compiled a second time with -DB2R_REAL_IS_DOUBLE (plan-time JIT only) for -p 1.
+namespace b2r {
+#if defined(B2R_REAL_IS_DOUBLE)
+typedef double real;
+typedef double2 real2;
+B2R_HD real2 make_real2(real x, real y) { return make_double2(x, y); }
+B2R_HD real rfma(real a, real b, real c) { return fma(a, b, c); }
+B2R_HD real real_sqrt(real a) { return sqrt(a); }
+#if defined(B2R_HOST_EMU)
+B2R_HD real real_sinpi(real a) { return std::sin(3.14159265358979323846 * a); }
+#else
+B2R_HD real real_sinpi(real a) { return sinpi(a); }
+#endif
+#else
+typedef float real;
+typedef float2 real2;
+B2R_HD real2 make_real2(real x, real y) { return make_float2(x, y); }
+B2R_HD real rfma(real a, real b, real c) { return fmaf(a, b, c); }
+B2R_HD real real_sqrt(real a) { return sqrtf(a); }
+B2R_HD real real_sinpi(real a) { return sinpif(a); }
+#endif
+}  // namespace b2r

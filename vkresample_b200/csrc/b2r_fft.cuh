@@ -24,17 +24,17 @@
 namespace b2r {
 
 // ------------------------------------------------------------------ complex helpers
-B2R_DEV float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
-B2R_DEV float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
-B2R_DEV float2 cmul(float2 a, float2 b) {
-    return make_float2(fmaf(-a.y, b.y, a.x * b.x), fmaf(a.y, b.x, a.x * b.y));
+B2R_DEV real2 cadd(real2 a, real2 b) { return make_real2(a.x + b.x, a.y + b.y); }
+B2R_DEV real2 csub(real2 a, real2 b) { return make_real2(a.x - b.x, a.y - b.y); }
+B2R_DEV real2 cmul(real2 a, real2 b) {
+    return make_real2(rfma(-a.y, b.y, a.x * b.x), rfma(a.y, b.x, a.x * b.y));
 }
-B2R_DEV float2 cscale(float2 a, float s) { return make_float2(a.x * s, a.y * s); }
-B2R_DEV float2 cconj(float2 a) { return make_float2(a.x, -a.y); }
+B2R_DEV real2 cscale(real2 a, real s) { return make_real2(a.x * s, a.y * s); }
+B2R_DEV real2 cconj(real2 a) { return make_real2(a.x, -a.y); }
 // multiply by DIR * i  (a quarter turn in the transform's direction)
-template <int DIR> B2R_DEV float2 rotq(float2 a) {
-    if constexpr (DIR < 0) return make_float2(a.y, -a.x);
-    else return make_float2(-a.y, a.x);
+template <int DIR> B2R_DEV real2 rotq(real2 a) {
+    if constexpr (DIR < 0) return make_real2(a.y, -a.x);
+    else return make_real2(-a.y, a.x);
 }
 
 // ------------------------------------------------------------------ compile-time trig
@@ -72,71 +72,71 @@ constexpr double sin2pi(long num, long den) { return cos2pi(4 * num - den, 4 * d
 }  // namespace cx
 
 // v * exp(DIR * 2*pi*i * NUM/DEN) with the trivial rotations folded at compile time
-template <int NUM, int DEN, int DIR> B2R_DEV float2 cmul_root(float2 v) {
+template <int NUM, int DEN, int DIR> B2R_DEV real2 cmul_root(real2 v) {
     constexpr int n = ((NUM % DEN) + DEN) % DEN;
     if constexpr (n == 0) return v;
     else if constexpr (4 * n == DEN) return rotq<DIR>(v);
-    else if constexpr (2 * n == DEN) return make_float2(-v.x, -v.y);
+    else if constexpr (2 * n == DEN) return make_real2(-v.x, -v.y);
     else if constexpr (4 * n == 3 * DEN) return rotq<-DIR>(v);
     else if constexpr ((8 * n) % DEN == 0) {
-        constexpr float h = 0.70710678118654752440f;
+        constexpr real h = real(0.70710678118654752440);
         constexpr int o = (8 * n) / DEN;  // 1,3,5,7
         // exp(i*d*o*pi/4), d = DIR
-        constexpr float cr = (o == 1 || o == 7) ? h : -h;
-        constexpr float ci = ((o == 1 || o == 3) ? h : -h) * float(DIR);
-        return make_float2(cr * v.x - ci * v.y, cr * v.y + ci * v.x);
+        constexpr real cr = (o == 1 || o == 7) ? h : -h;
+        constexpr real ci = ((o == 1 || o == 3) ? h : -h) * real(DIR);
+        return make_real2(cr * v.x - ci * v.y, cr * v.y + ci * v.x);
     } else {
-        constexpr float cr = float(cx::cos2pi(n, DEN));
-        constexpr float ci = float(cx::sin2pi(n, DEN)) * float(DIR);
-        return make_float2(fmaf(-ci, v.y, cr * v.x), fmaf(ci, v.x, cr * v.y));
+        constexpr real cr = real(cx::cos2pi(n, DEN));
+        constexpr real ci = real(cx::sin2pi(n, DEN)) * real(DIR);
+        return make_real2(rfma(-ci, v.y, cr * v.x), rfma(ci, v.x, cr * v.y));
     }
 }
 
 // ------------------------------------------------------------------ prime / radix-4 butterflies
 // All operate in place on references and leave X[k] in the k-th argument (natural order).
-template <int DIR> B2R_DEV void dft2(float2& a, float2& b) {
-    float2 t = csub(a, b); a = cadd(a, b); b = t;
+template <int DIR> B2R_DEV void dft2(real2& a, real2& b) {
+    real2 t = csub(a, b); a = cadd(a, b); b = t;
 }
-template <int DIR> B2R_DEV void dft3(float2& a, float2& b, float2& c) {
-    constexpr float s3 = 0.86602540378443864676f;
-    float2 t = cadd(b, c);
-    float2 u = cscale(rotq<DIR>(csub(b, c)), s3);
-    float2 m = make_float2(fmaf(-0.5f, t.x, a.x), fmaf(-0.5f, t.y, a.y));
+template <int DIR> B2R_DEV void dft3(real2& a, real2& b, real2& c) {
+    constexpr real s3 = real(0.86602540378443864676);
+    real2 t = cadd(b, c);
+    real2 u = cscale(rotq<DIR>(csub(b, c)), s3);
+    real2 m = make_real2(rfma(real(-0.5), t.x, a.x), rfma(real(-0.5), t.y, a.y));
     a = cadd(a, t); b = cadd(m, u); c = csub(m, u);
 }
-template <int DIR> B2R_DEV void dft4(float2& a, float2& b, float2& c, float2& d) {
-    float2 s0 = cadd(a, c), d0 = csub(a, c), s1 = cadd(b, d), d1 = rotq<DIR>(csub(b, d));
+template <int DIR> B2R_DEV void dft4(real2& a, real2& b, real2& c, real2& d) {
+    real2 s0 = cadd(a, c), d0 = csub(a, c), s1 = cadd(b, d), d1 = rotq<DIR>(csub(b, d));
     a = cadd(s0, s1); c = csub(s0, s1); b = cadd(d0, d1); d = csub(d0, d1);
 }
-template <int DIR> B2R_DEV void dft5(float2& a, float2& b, float2& c, float2& d, float2& e) {
-    constexpr float c1 = float(cx::cos2pi(1, 5)), c2 = float(cx::cos2pi(2, 5));
-    constexpr float s1 = float(cx::sin2pi(1, 5)), s2 = float(cx::sin2pi(2, 5));
-    float2 t1 = cadd(b, e), t2 = cadd(c, d), t3 = csub(b, e), t4 = csub(c, d);
-    float2 m1 = make_float2(fmaf(c2, t2.x, fmaf(c1, t1.x, a.x)), fmaf(c2, t2.y, fmaf(c1, t1.y, a.y)));
-    float2 m2 = make_float2(fmaf(c1, t2.x, fmaf(c2, t1.x, a.x)), fmaf(c1, t2.y, fmaf(c2, t1.y, a.y)));
-    float2 n1 = rotq<DIR>(make_float2(fmaf(s2, t4.x, s1 * t3.x), fmaf(s2, t4.y, s1 * t3.y)));
-    float2 n2 = rotq<DIR>(make_float2(fmaf(-s1, t4.x, s2 * t3.x), fmaf(-s1, t4.y, s2 * t3.y)));
+template <int DIR> B2R_DEV void dft5(real2& a, real2& b, real2& c, real2& d, real2& e) {
+    constexpr real c1 = real(cx::cos2pi(1, 5)), c2 = real(cx::cos2pi(2, 5));
+    constexpr real s1 = real(cx::sin2pi(1, 5)), s2 = real(cx::sin2pi(2, 5));
+    real2 t1 = cadd(b, e), t2 = cadd(c, d), t3 = csub(b, e), t4 = csub(c, d);
+    real2 m1 = make_real2(rfma(c2, t2.x, rfma(c1, t1.x, a.x)), rfma(c2, t2.y, rfma(c1, t1.y, a.y)));
+    real2 m2 = make_real2(rfma(c1, t2.x, rfma(c2, t1.x, a.x)), rfma(c1, t2.y, rfma(c2, t1.y, a.y)));
+    real2 n1 = rotq<DIR>(make_real2(rfma(s2, t4.x, s1 * t3.x), rfma(s2, t4.y, s1 * t3.y)));
+    real2 n2 = rotq<DIR>(make_real2(rfma(-s1, t4.x, s2 * t3.x), rfma(-s1, t4.y, s2 * t3.y)));
     a = cadd(a, cadd(t1, t2));
     b = cadd(m1, n1); e = csub(m1, n1); c = cadd(m2, n2); d = csub(m2, n2);
 }
 template <int DIR>
-B2R_DEV void dft7(float2& a, float2& b, float2& c, float2& d, float2& e, float2& f, float2& g) {
-    constexpr float c1 = float(cx::cos2pi(1, 7)), c2 = float(cx::cos2pi(2, 7)), c3 = float(cx::cos2pi(3, 7));
-    constexpr float s1 = float(cx::sin2pi(1, 7)), s2 = float(cx::sin2pi(2, 7)), s3 = float(cx::sin2pi(3, 7));
-    float2 t1 = cadd(b, g), t2 = cadd(c, f), t3 = cadd(d, e);
-    float2 u1 = csub(b, g), u2 = csub(c, f), u3 = csub(d, e);
-    float2 m1 = make_float2(fmaf(c3, t3.x, fmaf(c2, t2.x, fmaf(c1, t1.x, a.x))),
-                            fmaf(c3, t3.y, fmaf(c2, t2.y, fmaf(c1, t1.y, a.y))));
-    float2 m2 = make_float2(fmaf(c1, t3.x, fmaf(c3, t2.x, fmaf(c2, t1.x, a.x))),
-                            fmaf(c1, t3.y, fmaf(c3, t2.y, fmaf(c2, t1.y, a.y))));
-    float2 m3 = make_float2(fmaf(c2, t3.x, fmaf(c1, t2.x, fmaf(c3, t1.x, a.x))),
-                            fmaf(c2, t3.y, fmaf(c1, t2.y, fmaf(c3, t1.y, a.y))));
-    float2 n1 = rotq<DIR>(make_float2(fmaf(s3, u3.x, fmaf(s2, u2.x, s1 * u1.x)),
-                                      fmaf(s3, u3.y, fmaf(s2, u2.y, s1 * u1.y))));
-    float2 n2 = rotq<DIR>(make_float2(fmaf(-s1, u3.x, fmaf(-s3, u2.x, s2 * u1.x)),
-                                      fmaf(-s1, u3.y, fmaf(-s3, u2.y, s2 * u1.y))));
-    float2 n3 = rotq<DIR>(make_float2(fmaf(s2, u3.x, fmaf(-s1, u2.x, s3 * u1.x)),
-                                      fmaf(s2, u3.y, fmaf(-s1, u2.y, s3 * u1.y))));
+B2R_DEV void dft7(real2& a, real2& b, real2& c, real2& d, real2& e, real2& f, real2& g) {
+    constexpr real c1 = real(cx::cos2pi(1, 7)), c2 = real(cx::cos2pi(2, 7)), c3 = real(cx::cos2pi(3, 7));
+    constexpr real s1 = real(cx::sin2pi(1, 7)), s2 = real(cx::sin2pi(2, 7)), s3 = real(cx::sin2pi(3, 7));
+    real2 t1 = cadd(b, g), t2 = cadd(c, f), t3 = cadd(d, e);
+    real2 u1 = csub(b, g), u2 = csub(c, f), u3 = csub(d, e);
+    real2 m1 = make_real2(rfma(c3, t3.x, rfma(c2, t2.x, rfma(c1, t1.x, a.x))),
+                            rfma(c3, t3.y, rfma(c2, t2.y, rfma(c1, t1.y, a.y))));
+    real2 m2 = make_real2(rfma(c1, t3.x, rfma(c3, t2.x, rfma(c2, t1.x, a.x))),
+                            rfma(c1, t3.y, rfma(c3, t2.y, rfma(c2, t1.y, a.y))));
+    real2 m3 = make_real2(rfma(c2, t3.x, rfma(c1, t2.x, rfma(c3, t1.x, a.x))),
+                            rfma(c2, t3.y, rfma(c1, t2.y, rfma(c3, t1.y, a.y))));
+    real2 n1 = rotq<DIR>(make_real2(rfma(s3, u3.x, rfma(s2, u2.x, s1 * u1.x)),
+                                      rfma(s3, u3.y, rfma(s2, u2.y, s1 * u1.y))));
+    real2 n2 = rotq<DIR>(make_real2(rfma(-s1, u3.x, rfma(-s3, u2.x, s2 * u1.x)),
+                                      rfma(-s1, u3.y, rfma(-s3, u2.y, s2 * u1.y))));
+    real2 n3 = rotq<DIR>(make_real2(rfma(s2, u3.x, rfma(-s1, u2.x, s3 * u1.x)),
+                                      rfma(s2, u3.y, rfma(-s1, u2.y, s3 * u1.y))));
     a = cadd(a, cadd(t1, cadd(t2, t3)));
     b = cadd(m1, n1); g = csub(m1, n1);
     c = cadd(m2, n2); f = csub(m2, n2);
@@ -144,7 +144,7 @@ B2R_DEV void dft7(float2& a, float2& b, float2& c, float2& d, float2& e, float2&
 }
 
 // strided primitive dispatch on a register array (all indices fold after unrolling)
-template <int R, int STRIDE, int DIR> B2R_DEV void dft_prim(float2* v) {
+template <int R, int STRIDE, int DIR> B2R_DEV void dft_prim(real2* v) {
     if constexpr (R == 2) dft2<DIR>(v[0], v[STRIDE]);
     else if constexpr (R == 3) dft3<DIR>(v[0], v[STRIDE], v[2 * STRIDE]);
     else if constexpr (R == 4) dft4<DIR>(v[0], v[STRIDE], v[2 * STRIDE], v[3 * STRIDE]);
@@ -181,7 +181,7 @@ template <int I, int N, class F> B2R_DEV void static_for(F&& f) {
 }
 
 // In-register R-point DFT.  Input x[n] in v[n]; output X[k] in v[dft_slot<R>(k)].
-template <int R, int DIR> B2R_DEV void dft(float2 (&v)[R]) {
+template <int R, int DIR> B2R_DEV void dft(real2 (&v)[R]) {
     constexpr int r1 = RadixTraits<R>::r1, r2 = RadixTraits<R>::r2;
     if constexpr (r2 == 1) {
         dft_prim<R, 1, DIR>(v);
@@ -201,8 +201,8 @@ template <int R, int DIR> B2R_DEV void dft(float2 (&v)[R]) {
 }
 
 // v[i] *= w^i, i = 1..R-1, powers by a balanced multiplication tree (depth <= log2 R)
-template <int R> B2R_DEV void apply_twiddle_powers(float2 (&v)[R], float2 w) {
-    float2 pw[R];
+template <int R> B2R_DEV void apply_twiddle_powers(real2 (&v)[R], real2 w) {
+    real2 pw[R];
     pw[1] = w;
     static_for<2, R>([&](auto i) {
         constexpr int I = decltype(i)::value;
@@ -215,7 +215,7 @@ template <int R> B2R_DEV void apply_twiddle_powers(float2 (&v)[R], float2 w) {
 }
 
 // ------------------------------------------------------------------ shared-memory layout
-// One float2 of padding after every 16: keeps the stride-R writes of the early Stockham stages
+// One real2 of padding after every 16: keeps the stride-R writes of the early Stockham stages
 // and the contiguous reads of all stages free of bank conflicts for power-of-two radices.
 B2R_HD int smem_pad(int i) { return i + (i >> 4); }
 B2R_HD constexpr int smem_padded_len(int n) { return n + (n >> 4) + 1; }
@@ -295,15 +295,15 @@ template <int R_, int NB_> struct DynStage {
 
 // shared -> registers, outer twiddle w = exp(DIR*2*pi*i*p/(S*R)) (one table load), butterfly
 template <int DIR, int CS, class St>
-B2R_DEV void stage_load_compute(const St st, const float2* sm, const float2* __restrict__ tw, int T, int tid,
-                                int c, float2 (&v)[St::NB][St::R]) {
+B2R_DEV void stage_load_compute(const St st, const real2* sm, const real2* __restrict__ tw, int T, int tid,
+                                int c, real2 (&v)[St::NB][St::R]) {
     constexpr int R = St::R;
 #pragma unroll
     for (int b = 0; b < St::NB; ++b) {
         int j = tid + b * T;
         if (j < st.nb()) {
             if constexpr (St::template read_const<CS>()) {
-                const float2* base = sm + smem_pad(j * CS + c);
+                const real2* base = sm + smem_pad(j * CS + c);
                 const int step = st.nb() * CS + ((st.nb() * CS) >> 4);
 #pragma unroll
                 for (int i = 0; i < R; ++i) v[b][i] = base[i * step];
@@ -314,7 +314,7 @@ B2R_DEV void stage_load_compute(const St st, const float2* sm, const float2* __r
             if (st.stride() > 1) {
                 int q, p;
                 st.split(j, q, p);
-                float2 w = B2R_LDG(tw + st.tw_off() + p);
+                real2 w = B2R_LDG(tw + st.tw_off() + p);
                 if constexpr (DIR > 0) w.y = -w.y;
                 apply_twiddle_powers<R>(v[b], w);
             }
@@ -325,7 +325,7 @@ B2R_DEV void stage_load_compute(const St st, const float2* sm, const float2* __r
 
 // butterfly on values already in registers (first stage fed from global memory; S = 1: no twiddle)
 template <int DIR, class St>
-B2R_DEV void stage_compute_first(const St st, int T, int tid, float2 (&v)[St::NB][St::R]) {
+B2R_DEV void stage_compute_first(const St st, int T, int tid, real2 (&v)[St::NB][St::R]) {
 #pragma unroll
     for (int b = 0; b < St::NB; ++b) {
         int j = tid + b * T;
@@ -335,7 +335,7 @@ B2R_DEV void stage_compute_first(const St st, int T, int tid, float2 (&v)[St::NB
 
 // registers -> shared at the Stockham output index  p + (j div S)*S*R + k*S
 template <int CS, class St>
-B2R_DEV void stage_store(const St st, float2* sm, int T, int tid, int c, float2 (&v)[St::NB][St::R]) {
+B2R_DEV void stage_store(const St st, real2* sm, int T, int tid, int c, real2 (&v)[St::NB][St::R]) {
     constexpr int R = St::R;
 #pragma unroll
     for (int b = 0; b < St::NB; ++b) {
@@ -345,7 +345,7 @@ B2R_DEV void stage_store(const St st, float2* sm, int T, int tid, int c, float2 
             st.split(j, q, p);
             int base = q * st.stride() * R + p;
             if constexpr (St::template write_const<CS>()) {
-                float2* dst = sm + smem_pad(base * CS + c);
+                real2* dst = sm + smem_pad(base * CS + c);
                 static_for<0, R>([&](auto k) {
                     constexpr int K = decltype(k)::value;
                     const int off = K * st.stride() * CS;

@@ -134,8 +134,8 @@ void mkdirs(const std::string& p) {
 }
 
 // per-plan state: one module with the kernels this plan needs
-struct RowCtx { JitModule* m; CUfunction fn = nullptr, fn_c2c = nullptr; int threads = 0, ppb = 1; bool bulk = false; int sms = 0; };
-struct ColCtx { JitModule* m; CUfunction fn = nullptr; int threads = 0, cc = 4; };
+struct RowCtx { JitModule* m; CUfunction fn = nullptr, fn_c2c = nullptr; int threads = 0, ppb = 1; bool bulk = false; int sms = 0; bool dbl = false; };
+struct ColCtx { JitModule* m; CUfunction fn = nullptr; int threads = 0, cc = 4; bool dbl = false; };
 
 }  // namespace
 
@@ -143,6 +143,8 @@ struct JitModule {
     CUmodule mod = nullptr;
     RowCtx r2c, c2r;
     ColCtx cols;
+    CUfunction sharpen = nullptr, to_planar = nullptr, to_u8 = nullptr;
+    bool sharpen_rows = false;
 };
 
 bool jit_available(std::string* why) {
@@ -189,7 +191,8 @@ cudaError_t run_c2r(cudaStream_t s, const C2rArgs& a, int, size_t smem, const vo
     int pairs = 3 * a.dm.up_h / 2;
     char plan = 0;
     float scale = a.scale;
-    void* args[] = {(void*)&a.spec, (void*)&a.pre, (void*)&a.tw, &plan, (void*)&a.dm, &pairs, &scale};
+    double scale_d = 1.0 / (double)a.dm.up_w;
+    void* args[] = {(void*)&a.spec, (void*)&a.pre, (void*)&a.tw, &plan, (void*)&a.dm, &pairs, k->dbl ? (void*)&scale_d : (void*)&scale};
     unsigned grid = (unsigned)((pairs + k->ppb - 1) / k->ppb), by = (unsigned)k->ppb;
     if (k->bulk) {   // persistent: one CTA per resident slot
         int per_sm = 0;
@@ -204,7 +207,8 @@ cudaError_t run_c2c(cudaStream_t s, const C2rArgs& a, int, size_t smem, const vo
     int rows = 3 * a.dm.up_h;
     char plan = 0;
     float scale = a.scale;
-    void* args[] = {(void*)&a.spec, (void*)&a.nyq, (void*)&a.pre, (void*)&a.tw, &plan, (void*)&a.dm, &rows, &scale};
+    double scale_d = 1.0 / (double)a.dm.up_w;
+    void* args[] = {(void*)&a.spec, (void*)&a.nyq, (void*)&a.pre, (void*)&a.tw, &plan, (void*)&a.dm, &rows, k->dbl ? (void*)&scale_d : (void*)&scale};
     return cu2rt(api().cuLaunchKernel(k->fn_c2c, (rows + k->ppb - 1) / k->ppb, 1, 1, k->threads, k->ppb, 1, (unsigned)smem,
                                       (CUstream)s, args, nullptr));
 }
@@ -212,7 +216,9 @@ cudaError_t run_cols(cudaStream_t s, const ColsArgs& a, int, size_t smem, const 
     const ColCtx* k = static_cast<const ColCtx*>(ctx);
     char pf = 0, pi = 0;
     float scale = a.scale;
-    void* args[] = {(void*)&a.in, (void*)&a.out, (void*)&a.tw_f, (void*)&a.tw_i, &pf, &pi, (void*)&a.dm, &scale, (void*)&a.nyq};
+    double scale_d = 1.0 / (double)a.dm.up_h;
+    void* args[] = {(void*)&a.in, (void*)&a.out, (void*)&a.tw_f, (void*)&a.tw_i, &pf, &pi, (void*)&a.dm,
+                    k->dbl ? (void*)&scale_d : (void*)&scale, (void*)&a.nyq};
     return cu2rt(api().cuLaunchKernel(k->fn, (a.dm.nx + k->cc - 1) / k->cc, 3, 1, k->threads * k->cc, 1, 1, (unsigned)smem,
                                       (CUstream)s, args, nullptr));
 }
@@ -226,7 +232,9 @@ bool jit_build(const JitRequest& rq, JitModule** out_mod, RowImpl* r2c, ColImpl*
     if (hdr.empty()) { *err = "kernel headers not found next to the library (" + csrc + ")"; return false; }
 
     // ---- source: explicit instantiations of exactly the kernels this plan launches
-    const char* tin = rq.precision == 2 ? "__half" : "float";
+    const bool dbl = rq.precision == 1;
+    const size_t cb = dbl ? 16 : 8;   // bytes of one complex workspace element
+    const char* tin = rq.precision == 2 ? "__half" : (dbl ? "double" : "float");
     std::vector<std::string> names;   // name expressions, in the order r2c, cols, c2r, c2c
     const int ppb_w = std::max(1, std::min(8, 256 / rq.w.threads));
     const int ppb_uw = std::max(1, std::min(8, 256 / rq.uw.threads));
@@ -250,8 +258,15 @@ bool jit_build(const JitRequest& rq, JitModule** out_mod, RowImpl* r2c, ColImpl*
             names.push_back(m.str());
         }
     }
+    const bool rows_sharpen = (rq.up_w % 4) == 0;
+    if (rq.want_pixels) {
+        names.push_back(rows_sharpen ? std::string("b2r::k_sharpen_rows<") + tin + ", b2r::kSharpenRowsPerThread>"
+                                     : std::string("b2r::k_sharpen<") + tin + ", 4>");
+        names.push_back(std::string("b2r::k_u8_to_planar<") + tin + ">");
+        names.push_back(std::string("b2r::k_planar_to_u8<") + tin + ">");
+    }
     // name expressions instantiate the templates; the source only has to bring the templates in
-    std::string source = "#include \"b2r_kernels.cuh\"\n";
+    std::string source = dbl ? "#define B2R_REAL_IS_DOUBLE 1\n#include \"b2r_kernels.cuh\"\n" : "#include \"b2r_kernels.cuh\"\n";
     for (const auto& n : names) source += "// " + n + "\n";
 
     int vmaj = 0, vmin = 0;
@@ -314,35 +329,60 @@ bool jit_build(const JitRequest& rq, JitModule** out_mod, RowImpl* r2c, ColImpl*
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     bool ok = true;
     if (rq.want_r2c) {
-        m->r2c.m = m; m->r2c.threads = rq.w.threads; m->r2c.ppb = ppb_w;
+        m->r2c.m = m; m->r2c.threads = rq.w.threads; m->r2c.ppb = ppb_w; m->r2c.dbl = dbl;
         ok = ok && get(&m->r2c.fn);
         *r2c = RowImpl{};
         r2c->name = "r2c_rows<jit>"; r2c->is_static = true; r2c->is_jit = true; r2c->sched = rq.w; r2c->ppb = ppb_w;
-        r2c->smem = (size_t)ppb_w * smem_padded_len(rq.w.n) * sizeof(float2);
+        r2c->smem = (size_t)ppb_w * smem_padded_len(rq.w.n) * cb;
         r2c->ctx = &m->r2c; r2c->prepare = &prep_row; r2c->r2c = &run_r2c;
     }
     if (rq.want_cols) {
-        m->cols.m = m; m->cols.threads = rq.uh.threads; m->cols.cc = rq.cc;
+        m->cols.m = m; m->cols.threads = rq.uh.threads; m->cols.cc = rq.cc; m->cols.dbl = dbl;
         ok = ok && get(&m->cols.fn);
         *cols = ColImpl{};
         cols->name = "cols<jit>"; cols->is_static = true; cols->is_jit = true; cols->fwd = rq.h; cols->inv = rq.uh; cols->cc = rq.cc;
-        cols->smem = (size_t)smem_padded_len(rq.uh.n * rq.cc) * sizeof(float2);
+        cols->smem = (size_t)smem_padded_len(rq.uh.n * rq.cc) * cb;
         cols->ctx = &m->cols; cols->prepare = &prep_col; cols->launch = &run_cols;
     }
     if (rq.want_c2r) {
-        m->c2r.m = m; m->c2r.threads = rq.uw.threads; m->c2r.ppb = ppb_uw; m->c2r.bulk = true; m->c2r.sms = sms;
+        m->c2r.m = m; m->c2r.threads = rq.uw.threads; m->c2r.ppb = ppb_uw; m->c2r.bulk = true; m->c2r.sms = sms; m->c2r.dbl = dbl;
         ok = ok && get(&m->c2r.fn);
         if (rq.c2c) ok = ok && get(&m->c2r.fn_c2c);
         *c2r = RowImpl{};
         c2r->name = "c2r_rows_bulk<jit>"; c2r->is_static = true; c2r->is_jit = true; c2r->sched = rq.uw; c2r->ppb = 1;
-        c2r->smem = c2r_bulk_smem_bytes(rq.uw.n, rq.nx);
+        c2r->smem = 16 + 4 * (size_t)c2r_stage_row_elems(rq.nx) * cb + (size_t)smem_padded_len(rq.uw.n) * cb;
         c2r->ctx = &m->c2r; c2r->prepare = &prep_row; c2r->c2r = &run_c2r;
         c2r->c2c = &run_c2c; c2r->prepare_c2c = &prep_row_c2c; c2r->ppb_c2c = ppb_uw;
-        c2r->smem_c2c = (size_t)ppb_uw * smem_padded_len(rq.uw.n) * sizeof(float2);
+        c2r->smem_c2c = (size_t)ppb_uw * smem_padded_len(rq.uw.n) * cb;
+    }
+    if (rq.want_pixels) {
+        m->sharpen_rows = rows_sharpen;
+        ok = ok && get(&m->sharpen) && get(&m->to_planar) && get(&m->to_u8);
     }
     if (!ok) { *err = "a JIT-compiled kernel was not found in the module"; jit_destroy(m); return false; }
     *out_mod = m;
     return true;
+}
+
+cudaError_t jit_launch_sharpen(const JitModule* m, cudaStream_t s, const SharpenArgs& a) {
+    void* args[] = {(void*)&a.pre, (void*)&a.out, (void*)&a.dm};
+    if (m->sharpen_rows) {
+        const int bx = sharpen_rows_block(a.dm.up_w), ry = kSharpenRowsPerThread;
+        return cu2rt(api().cuLaunchKernel(m->sharpen, (a.dm.up_w / 4 + bx - 1) / bx, (a.dm.up_h + ry - 1) / ry, 3, bx, 1, 1, 0,
+                                          (CUstream)s, args, nullptr));
+    }
+    return cu2rt(api().cuLaunchKernel(m->sharpen, (a.dm.up_w + 4 * 256 - 1) / (4 * 256), a.dm.up_h, 3, 256, 1, 1, 0, (CUstream)s,
+                                      args, nullptr));
+}
+cudaError_t jit_launch_u8_to_planar(const JitModule* m, cudaStream_t s, const unsigned char* src, void* dst, const FrameDims& dm) {
+    const size_t n4 = ((size_t)dm.w * dm.h + 3) / 4;
+    void* args[] = {(void*)&src, (void*)&dst, (void*)&dm};
+    return cu2rt(api().cuLaunchKernel(m->to_planar, (unsigned)((n4 + 255) / 256), 1, 1, 256, 1, 1, 0, (CUstream)s, args, nullptr));
+}
+cudaError_t jit_launch_planar_to_u8(const JitModule* m, cudaStream_t s, const void* src, unsigned char* dst, const FrameDims& dm) {
+    const size_t n4 = ((size_t)dm.up_w * dm.up_h + 3) / 4;
+    void* args[] = {(void*)&src, (void*)&dst, (void*)&dm};
+    return cu2rt(api().cuLaunchKernel(m->to_u8, (unsigned)((n4 + 255) / 256), 1, 1, 256, 1, 1, 0, (CUstream)s, args, nullptr));
 }
 
 }  // namespace b2r

@@ -60,6 +60,7 @@ void build_fft(int n, const int* radices, int nst, int threads, HostFft* out) {
     d.nstages = nst;
     d.threads = threads;
     out->twiddles.clear();
+    out->twiddles_d.clear();
     int stride = 1;
     for (int s = 0; s < d.nstages; ++s) {
         StageDesc& sd = d.st[s];
@@ -75,6 +76,8 @@ void build_fft(int n, const int* radices, int nst, int threads, HostFft* out) {
             for (int p = 0; p < stride; ++p) {
                 double a = -2.0 * M_PI * (double)p / m;
                 out->twiddles.push_back(make_float2((float)std::cos(a), (float)std::sin(a)));
+                // double table: exact octant reduction (the same routine the in-kernel constants use)
+                out->twiddles_d.push_back(make_double2(cx::cos2pi(-p, (long)m), cx::sin2pi(-p, (long)m)));
             }
         }
         stride *= sd.radix;
@@ -96,8 +99,8 @@ bool make_geometry(int w, int h, float upscale, int precision, float sharpen, Ge
     auto fail = [&](const std::string& m) { if (err) *err = m; return false; };
     if (w < 4 || h < 4 || (w & 1) || (h & 1)) return fail("input width and height must be even and >= 4");
     if (!(upscale >= 1.0f)) return fail("upscale factor must be >= 1");
-    if (precision != 0 && precision != 2)
-        return fail("precision must be 0 (fp32) or 2 (fp16 storage); 1 (double) is not supported");
+    if (precision != 0 && precision != 1 && precision != 2)
+        return fail("precision must be 0 (fp32), 1 (fp64) or 2 (fp16 storage)");
     Geometry r;
     r.w = w; r.h = h; r.upscale = upscale; r.precision = precision; r.sharpen = sharpen;
     // float products truncated on assignment to uint32_t, as the reference does

@@ -19,6 +19,7 @@ namespace b2r {
 struct HostFft {
     FftDesc desc{};
     std::vector<float2> twiddles;  // concatenated per-stage rows, forward sign
+    std::vector<double2> twiddles_d;  // the same in double (for -p 1)
 };
 
 // Factor n (= 2^a 3^b 5^c 7^d, the set the reference accepts: vkFFT.h:4719-4726) into radices
@@ -39,7 +40,7 @@ struct Geometry {
     int spec_stride = 0;       // row stride (complex elements) of both spectrum buffers
     int zp_lo = 0, zp_hi = 0;  // inverse reads rows [zp_lo, zp_hi) as zero, VkResample.cpp:1494-1495
     int neg_shift = 0;         // rows >= up_h - h/2 come from source row (m - neg_shift)
-    int precision = 0;         // 0 fp32, 2 fp16 storage
+    int precision = 0;         // 0 fp32, 1 fp64, 2 fp16 storage
     float up2 = 1.f;           // appSharpen.upscale, VkResample.cpp:1615
     float sharpen = 0.2f;
     // strides in elements (float or half)
@@ -47,7 +48,8 @@ struct Geometry {
     size_t pre_row = 0, pre_plane = 0;  // upW, (upW+2)*upH                VkResample.cpp:1593-1596
     size_t out_row = 0, out_plane = 0;  // upW, upW*upH (compact)          VkResample.cpp:1599-1601
     size_t pre_elems = 0;               // allocation incl. zero slack after the last plane
-    size_t elem_bytes() const { return precision == 2 ? 2 : 4; }
+    size_t elem_bytes() const { return precision == 2 ? 2 : (precision == 1 ? 8 : 4); }
+    size_t cplx_bytes() const { return precision == 1 ? 16 : 8; }   // one spectrum / workspace element
     size_t input_bytes() const { return 3 * in_plane * elem_bytes(); }      // == 3*cs*(W/2+1)*H
     size_t output_bytes() const { return 3 * out_plane * elem_bytes(); }    // VkResample.cpp:1698
     size_t spec_in_elems() const { return 3ull * h * spec_stride; }

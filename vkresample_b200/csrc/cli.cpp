@@ -259,7 +259,7 @@ int main(int argc, char* argv[]) {
                "\t-devices: print the list of available GPU devices\n"
                "\t-d X: select GPU device (default 0)\n"
                "\t-u X: specify upscale factor (float, X>=1)\n"
-               "\t-p X: specify precision (0 - single (default), 2 - half storage; 1 - double is not supported)\n"
+               "\t-p X: specify precision (0 - single (default), 1 - double, 2 - half storage)\n"
                "\t-s X: specify sharpen constant (default 0.2)\n"
                "\t-n X: specify how many times to perform upscale. This removes dispatch overhead and will show the real application performance (default 1)\n"
                "\t-i NAME: specify input png file path\n"
