@@ -198,8 +198,14 @@ static void emu_sharpen(const FrameDims dm, int precision, const void* pre, void
         constexpr int RY = kSharpenRowsPerThread;
         block.x = bx; grid.x = (dm.up_w / 4 + bx - 1) / bx; grid.y = (dm.up_h + RY - 1) / RY; grid.z = 3;
         b2r_emu::launch(grid, block, 0, [&] {
-            if (precision == 2) k_sharpen_rows<__half, RY>((const __half*)pre, (__half*)out, dm);
-            else k_sharpen_rows<float, RY>((const float*)pre, (float*)out, dm);
+            const bool ragged = sharpen_rows_ragged(dm.up_w, bx);
+            if (precision == 2) {
+                if (ragged) k_sharpen_rows<__half, RY, true>((const __half*)pre, (__half*)out, dm);
+                else k_sharpen_rows<__half, RY, false>((const __half*)pre, (__half*)out, dm);
+            } else {
+                if (ragged) k_sharpen_rows<float, RY, true>((const float*)pre, (float*)out, dm);
+                else k_sharpen_rows<float, RY, false>((const float*)pre, (float*)out, dm);
+            }
         });
         return;
     }

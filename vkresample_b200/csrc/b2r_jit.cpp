@@ -15,6 +15,7 @@
 
 #include <dlfcn.h>
 #include <sys/stat.h>
+#include <unistd.h>
 
 #include <cstdio>
 #include <cstdlib>
@@ -260,7 +261,9 @@ bool jit_build(const JitRequest& rq, JitModule** out_mod, RowImpl* r2c, ColImpl*
     }
     const bool rows_sharpen = (rq.up_w % 4) == 0;
     if (rq.want_pixels) {
-        names.push_back(rows_sharpen ? std::string("b2r::k_sharpen_rows<") + tin + ", b2r::kSharpenRowsPerThread>"
+        const bool ragged = rows_sharpen && sharpen_rows_ragged(rq.up_w, sharpen_rows_block(rq.up_w));
+        names.push_back(rows_sharpen ? std::string("b2r::k_sharpen_rows<") + tin + ", b2r::kSharpenRowsPerThread, " +
+                                           (ragged ? "true>" : "false>")
                                      : std::string("b2r::k_sharpen<") + tin + ", 4>");
         names.push_back(std::string("b2r::k_u8_to_planar<") + tin + ">");
         names.push_back(std::string("b2r::k_planar_to_u8<") + tin + ">");
@@ -314,10 +317,22 @@ bool jit_build(const JitRequest& rq, JitModule** out_mod, RowImpl* r2c, ColImpl*
         cubin.resize(cs);
         a.nvrtcGetCUBIN(prog, &cubin[0]);
         a.nvrtcDestroyProgram(&prog);
+        // publish atomically (several worker threads / processes may build the same key at once):
+        // write to a private name, then rename; the .names file goes last and gates the cache hit
         mkdirs(cache_dir());
-        std::ofstream(cpath, std::ios::binary).write(cubin.data(), (std::streamsize)cubin.size());
-        std::ofstream nf(npath);
-        for (const auto& l : lowered) nf << l << "\n";
+        const std::string tag = "." + std::to_string((long long)getpid()) + "." + std::to_string((unsigned long long)(uintptr_t)&cubin);
+        {
+            std::ofstream cf(cpath + tag, std::ios::binary);
+            cf.write(cubin.data(), (std::streamsize)cubin.size());
+        }
+        {
+            std::ofstream nf(npath + tag);
+            for (const auto& l : lowered) nf << l << "\n";
+        }
+        if (rename((cpath + tag).c_str(), cpath.c_str()) != 0 || rename((npath + tag).c_str(), npath.c_str()) != 0) {
+            remove((cpath + tag).c_str());
+            remove((npath + tag).c_str());
+        }
     }
 
     JitModule* m = new JitModule();

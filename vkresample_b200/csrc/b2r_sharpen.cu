@@ -7,10 +7,14 @@ cudaError_t launch_sharpen_kernel(cudaStream_t s, const SharpenArgs& a) {
     if (bx > 0) {   // vectorised rolling-window kernel
         constexpr int RY = kSharpenRowsPerThread;
         dim3 block(bx), grid((a.dm.up_w / 4 + bx - 1) / bx, (a.dm.up_h + RY - 1) / RY, 3);
-        if (a.precision == 2)
-            k_sharpen_rows<__half, RY><<<grid, block, 0, s>>>((const __half*)a.pre, (__half*)a.out, a.dm);
-        else
-            k_sharpen_rows<float, RY><<<grid, block, 0, s>>>((const float*)a.pre, (float*)a.out, a.dm);
+        const bool ragged = sharpen_rows_ragged(a.dm.up_w, bx);
+        if (a.precision == 2) {
+            if (ragged) k_sharpen_rows<__half, RY, true><<<grid, block, 0, s>>>((const __half*)a.pre, (__half*)a.out, a.dm);
+            else k_sharpen_rows<__half, RY, false><<<grid, block, 0, s>>>((const __half*)a.pre, (__half*)a.out, a.dm);
+        } else {
+            if (ragged) k_sharpen_rows<float, RY, true><<<grid, block, 0, s>>>((const float*)a.pre, (float*)a.out, a.dm);
+            else k_sharpen_rows<float, RY, false><<<grid, block, 0, s>>>((const float*)a.pre, (float*)a.out, a.dm);
+        }
         return cudaGetLastError();
     }
     constexpr int PX = 4;   // any-width fallback
