@@ -41,9 +41,10 @@ def test_unschedulable_sizes_rejected():
         assert eu.schedule(n)[0] is None
 
 
-@pytest.mark.parametrize("n", [256, 512, 1024, 2048, 4096, 1920, 3840, 7680, 640, 960, 1280, 2560, 5120])
+@pytest.mark.parametrize("n", [256, 512, 1024, 2048, 4096, 1920, 3840, 7680, 640, 960, 1280, 2560, 5120, 4320])
 def test_static_schedules(n):
-    """the ahead-of-time schedules of the BASELINE sizes (b2r_static_sizes.h)"""
+    """the ahead-of-time schedules of the BASELINE sizes (b2r_static_sizes.h); 7680 = 24*20*16 and
+    4320 = 18*16*15 exercise the nested composite radices (3x(2x4), 4x5, 2x(3x3))"""
     rng = np.random.default_rng(n)
     x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
     for d in (-1, 1):

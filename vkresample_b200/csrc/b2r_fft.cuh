@@ -155,7 +155,9 @@ template <int R, int STRIDE, int DIR> B2R_DEV void dft_prim(real2* v) {
 }
 
 // ------------------------------------------------------------------ radix traits
-// A radix is either primitive (2,3,4,5,7) or composite R = R1*R2 with primitive R1, R2.
+// A radix is either primitive (2,3,4,5,7) or composite R = R1*R2 with primitive R1 and R2 primitive or
+// itself composite (18 = 2 x (3x3), 24 = 3 x (2x4): used by the ahead-of-time / JIT schedules of long
+// transforms to save a whole shared-memory stage; the dynamic dispatcher stops at 16).
 template <int R> struct RadixTraits { static constexpr int r1 = R, r2 = 1; };
 template <> struct RadixTraits<6>  { static constexpr int r1 = 2, r2 = 3; };
 template <> struct RadixTraits<8>  { static constexpr int r1 = 2, r2 = 4; };
@@ -165,12 +167,15 @@ template <> struct RadixTraits<12> { static constexpr int r1 = 3, r2 = 4; };
 template <> struct RadixTraits<14> { static constexpr int r1 = 2, r2 = 7; };
 template <> struct RadixTraits<15> { static constexpr int r1 = 3, r2 = 5; };
 template <> struct RadixTraits<16> { static constexpr int r1 = 4, r2 = 4; };
+template <> struct RadixTraits<18> { static constexpr int r1 = 2, r2 = 9; };
+template <> struct RadixTraits<20> { static constexpr int r1 = 4, r2 = 5; };
+template <> struct RadixTraits<24> { static constexpr int r1 = 3, r2 = 8; };
 
 // register slot that holds output bin k after dft<R>
 template <int R> B2R_HD constexpr int dft_slot(int k) {
     constexpr int r1 = RadixTraits<R>::r1, r2 = RadixTraits<R>::r2;
-    if (r2 == 1) return k;
-    return (k % r1) * r2 + (k / r1);
+    if constexpr (r2 == 1) return k;
+    else return (k % r1) * r2 + dft_slot<r2>(k / r1);   // X[k1 + r1*k2] sits in sub-array k1 at the slot of k2
 }
 
 template <int I, int N, class F> B2R_DEV void static_for(F&& f) {
@@ -195,8 +200,10 @@ template <int R, int DIR> B2R_DEV void dft(real2 (&v)[R]) {
                 v[K1 * r2 + N2] = cmul_root<K1 * N2, R, DIR>(v[K1 * r2 + N2]);
             });
         });
-        // step 3: r2-point DFTs over n2 (contiguous) -> X[k1 + r1*k2] in v[k1*r2 + k2]
-        static_for<0, r1>([&](auto k1) { dft_prim<r2, 1, DIR>(v + decltype(k1)::value * r2); });
+        // step 3: r2-point DFTs over n2 (contiguous) -> X[k1 + r1*k2] in v[k1*r2 + dft_slot<r2>(k2)]
+        static_for<0, r1>([&](auto k1) {
+            dft<r2, DIR>(*reinterpret_cast<real2(*)[r2]>(v + decltype(k1)::value * r2));
+        });
     }
 }
 

@@ -23,12 +23,13 @@
     X(4096, 1, 256, 16, 16, 16)         \
     X(1920, 2, 128, 16, 15, 8)          \
     X(3840, 1, 256, 16, 16, 15)         \
-    X(7680, 1, 512, 16, 16, 15, 2)      \
+    X(7680, 1, 480, 24, 20, 16)         \
     X(640, 4, 64, 16, 8, 5)             \
     X(960, 4, 64, 16, 15, 4)            \
     X(1280, 2, 96, 16, 16, 5)           \
     X(2560, 1, 256, 16, 16, 10)         \
-    X(5120, 1, 352, 16, 16, 5, 4)
+    X(5120, 1, 352, 16, 16, 5, 4)       \
+    X(4320, 1, 288, 18, 16, 15)
 
 namespace b2r {
 using ColF128 = StaticFft<128, 16, 16, 8>;
@@ -39,7 +40,7 @@ using ColF1024 = StaticFft<1024, 128, 16, 16, 4>;
 using ColI2048 = StaticFft<2048, 128, 16, 16, 8>;
 using ColF1080 = StaticFft<1080, 180, 15, 12, 6>;
 using ColI2160 = StaticFft<2160, 180, 15, 12, 12>;
-using ColF2160 = StaticFft<2160, 360, 15, 12, 12>;
+using ColF2160 = StaticFft<2160, 288, 15, 12, 12>;
 using ColF360 = StaticFft<360, 48, 15, 8, 3>;
 using ColI720 = StaticFft<720, 48, 16, 15, 3>;
 using ColF540 = StaticFft<540, 90, 15, 12, 3>;
@@ -48,7 +49,7 @@ using ColF720 = StaticFft<720, 120, 16, 15, 3>;
 using ColI1440 = StaticFft<1440, 120, 16, 15, 6>;
 using ColF1440 = StaticFft<1440, 240, 16, 15, 6>;
 using ColI2880 = StaticFft<2880, 240, 16, 15, 12>;
-using ColI4320 = StaticFft<4320, 360, 16, 15, 6, 3>;
+using ColI4320 = StaticFft<4320, 288, 18, 16, 15>;
 }  // namespace b2r
 
 #define B2R_STATIC_COLS(X)                     \
