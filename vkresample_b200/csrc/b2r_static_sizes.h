@@ -40,7 +40,6 @@ using ColF1024 = StaticFft<1024, 128, 16, 16, 4>;
 using ColI2048 = StaticFft<2048, 128, 16, 16, 8>;
 using ColF1080 = StaticFft<1080, 180, 15, 12, 6>;
 using ColI2160 = StaticFft<2160, 180, 15, 12, 12>;
-using ColF2160 = StaticFft<2160, 288, 15, 12, 12>;
 using ColF360 = StaticFft<360, 48, 15, 8, 3>;
 using ColI720 = StaticFft<720, 48, 16, 15, 3>;
 using ColF540 = StaticFft<540, 90, 15, 12, 3>;
@@ -49,7 +48,12 @@ using ColF720 = StaticFft<720, 120, 16, 15, 3>;
 using ColI1440 = StaticFft<1440, 120, 16, 15, 6>;
 using ColF1440 = StaticFft<1440, 240, 16, 15, 6>;
 using ColI2880 = StaticFft<2880, 240, 16, 15, 12>;
-using ColI4320 = StaticFft<4320, 288, 18, 16, 15>;
+// 4-column tile (32 B = one DRAM sector per spectrum row), two butterflies per thread: 193 us against
+// 312 us for <4320, 288, ...> with 2 columns per CTA (one CTA per SM either way)
+using ColF2160 = StaticFft<2160, 144, 15, 16, 9>;
+using ColI4320 = StaticFft<4320, 144, 18, 16, 15>;
+using ColF2160n = StaticFft<2160, 288, 15, 12, 12>;
+using ColI4320n = StaticFft<4320, 288, 18, 16, 15>;
 }  // namespace b2r
 
 #define B2R_STATIC_COLS(X)                     \
@@ -57,7 +61,7 @@ using ColI4320 = StaticFft<4320, 288, 18, 16, 15>;
     X(512, 1024, 4, ColF512, ColI1024)         \
     X(1024, 2048, 4, ColF1024, ColI2048)       \
     X(1080, 2160, 4, ColF1080, ColI2160)       \
-    X(2160, 4320, 2, ColF2160, ColI4320)       \
+    X(2160, 4320, 4, ColF2160, ColI4320)       \
     X(360, 720, 8, ColF360, ColI720)           \
     X(540, 1080, 4, ColF540, ColI1080)         \
     X(720, 1440, 4, ColF720, ColI1440)         \
@@ -66,4 +70,5 @@ using ColI4320 = StaticFft<4320, 288, 18, 16, 15>;
 // extra tile widths of the c2 column kernel, selectable with B2R_COLS_CC for tuning runs
 #define B2R_STATIC_COLS_TUNING(X)              \
     X(1024, 2048, 2, ColF1024, ColI2048)       \
-    X(1024, 2048, 8, ColF1024, ColI2048)
+    X(1024, 2048, 8, ColF1024, ColI2048)       \
+    X(2160, 4320, 2, ColF2160n, ColI4320n)
