@@ -156,6 +156,33 @@ def test_sharpen_constants_and_zero():
         _check(512, 256, 2.0, 2, s, "noise", e2e_tol=float("inf"))
 
 
+@pytest.mark.parametrize("w,h,up,prec,kind", [(2048, 1024, 2.0, 0, "noise"), (256, 128, 2.0, 0, "u8"), (1920, 1080, 2.0, 2, "noise"),
+                                              (700, 480, 1.5, 0, "noise"), (128, 64, 2.0, 0, "black_white")])
+def test_fast_sharpen_flag(w, h, up, prec, kind):
+    """B2R_FLAG_FAST_SHARPEN: approximate (<= 2 ulp) divisions / sqrt instead of the correctly rounded ones.
+    Same pre-sharpen plane (bit for bit); output within 2e-6 (fp32) / 2 half steps (fp16) of the default
+    path and of the oracle's sharpen on that plane, for the reference's default constant and the
+    largest one the fast paths serve (0.24); saturated and all-black regions included."""
+    x = vo.synthetic_frame("noise" if kind == "black_white" else kind, w, h, 7)
+    if kind == "black_white":            # exact 0 / 1 plateaus: x/0, 0/x, sqrt(0) cases of the approximations
+        x[:, : h // 2, :] = 0.0
+        x[:, h // 2:, : w // 2] = 1.0
+        x[2] = 0.0                      # a channel that is exactly zero everywhere (max == 0 -> 1/0)
+    dt = np.float16 if prec == 2 else np.float32
+    for s in (0.2, 0.24, 0.0):
+        with vb.Plan(w, h, up, prec, s) as p0, vb.Plan(w, h, up, prec, s, flags=vb.FLAG_FAST_SHARPEN) as p1:
+            o0 = p0.upscale(x.astype(dt)).copy(); pre0 = p0.download_pre_sharpen()
+            o1 = p1.upscale(x.astype(dt)).copy(); pre1 = p1.download_pre_sharpen()
+        assert _same_bits(pre0, pre1)
+        sh_o = vo.sharpen(pre1, vo.make_plan(w, h, up), s, prec)
+        assert _same_bits(sh_o, o0)
+        assert np.isfinite(o1).all()
+        d = np.abs(o1.astype(np.float64) - o0.astype(np.float64)).max()
+        print(f"\n[fast sharpen] {w}x{h} p={prec} s={s} {kind}: max-abs vs exact {d:.3e}, "
+              f"identical {np.mean(o1 == o0) * 100:.2f} %")
+        assert d <= (2e-6 if prec == 0 else 2 * 2.0 ** -11), d
+
+
 def test_execute_is_idempotent_and_timed():
     """-n semantics (VkResample.cpp:1260-1278): repeated execution on the resident input gives
     the same output; buffers persist across iterations and frames"""

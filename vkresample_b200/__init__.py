@@ -27,6 +27,7 @@ FLAG_NO_SHARPEN_LITERAL_ROUNDING = 2
 FLAG_C2C_PARITY = 4
 FLAG_JIT = 8
 FLAG_NO_JIT = 16
+FLAG_FAST_SHARPEN = 32   # approximate (<= 2 ulp) divisions / sqrt in the sharpen, see b2resample.h
 
 # every symbol include/b2resample.h declares (checked by tests/test_abi.py)
 EXPORTS = [

@@ -27,6 +27,7 @@ struct C2rArgs {
 };
 struct SharpenArgs {
     const void* pre; void* out; FrameDims dm; int precision;
+    bool approx = false;   // B2R_FLAG_FAST_SHARPEN
 };
 
 struct Schedule {      // radix list + cooperating threads of one transform

@@ -1,5 +1,6 @@
 // b2r_sharpen.cu -- launchers of K8 (CAS-style sharpen) and of the u8 pixel-format kernels (b2r_kernels.cuh).
 #include "b2r_launch.h"
+#include <type_traits>
 
 namespace b2r {
 cudaError_t launch_sharpen_kernel(cudaStream_t s, const SharpenArgs& a) {
@@ -8,13 +9,16 @@ cudaError_t launch_sharpen_kernel(cudaStream_t s, const SharpenArgs& a) {
         constexpr int RY = kSharpenRowsPerThread;
         dim3 block(bx), grid((a.dm.up_w / 4 + bx - 1) / bx, (a.dm.up_h + RY - 1) / RY, 3);
         const bool ragged = sharpen_rows_ragged(a.dm.up_w, bx);
-        if (a.precision == 2) {
-            if (ragged) k_sharpen_rows<__half, RY, true><<<grid, block, 0, s>>>((const __half*)a.pre, (__half*)a.out, a.dm);
-            else k_sharpen_rows<__half, RY, false><<<grid, block, 0, s>>>((const __half*)a.pre, (__half*)a.out, a.dm);
-        } else {
-            if (ragged) k_sharpen_rows<float, RY, true><<<grid, block, 0, s>>>((const float*)a.pre, (float*)a.out, a.dm);
-            else k_sharpen_rows<float, RY, false><<<grid, block, 0, s>>>((const float*)a.pre, (float*)a.out, a.dm);
-        }
+        auto go = [&](auto tp, auto rg, auto ap) {
+            using TP = decltype(tp);
+            k_sharpen_rows<TP, RY, decltype(rg)::value, decltype(ap)::value><<<grid, block, 0, s>>>((const TP*)a.pre, (TP*)a.out, a.dm);
+        };
+        auto pick = [&](auto tp) {
+            using T = std::true_type; using F = std::false_type;
+            if (ragged) { if (a.approx) go(tp, T{}, T{}); else go(tp, T{}, F{}); }
+            else        { if (a.approx) go(tp, F{}, T{}); else go(tp, F{}, F{}); }
+        };
+        if (a.precision == 2) pick(__half{}); else pick(float{});
         return cudaGetLastError();
     }
     constexpr int PX = 4;   // any-width fallback

@@ -174,7 +174,7 @@ static bool write_rgb(const char* path, const unsigned char* rgb, int w, int h) 
 // ------------------------------------------------------------------------------------------- CLI
 struct Config {  // VkResampleConfiguration, VkResample.cpp:45-59
     uint32_t device_id = 0, upload_files = 0, num_iter = 1, precision = 0, num_threads = 1, thread_id = 0;
-    uint32_t num_files = 1, gpus = 1, c2c = 0;
+    uint32_t num_files = 1, gpus = 1, c2c = 0, fast = 0;
     float upscale = 1.0f, sharpen = 0.2f;
     const char* input = nullptr;
     const char* output = nullptr;
@@ -207,7 +207,7 @@ static int launch_resample(Config cfg) {
 
     b2r_plan* plan = nullptr;
     int rc = b2r_plan_create(&plan, device, (uint32_t)w, (uint32_t)h, cfg.upscale, cfg.precision, cfg.sharpen,
-                             cfg.c2c ? B2R_FLAG_C2C_PARITY : B2R_FLAG_NONE);
+                             (cfg.c2c ? B2R_FLAG_C2C_PARITY : B2R_FLAG_NONE) | (cfg.fast ? B2R_FLAG_FAST_SHARPEN : B2R_FLAG_NONE));
     if (rc) { printf("Plan creation failed, error code: %d (%s)\n", rc, b2r_last_error()); return rc; }
     b2r_plan_info info;
     b2r_plan_get_info(plan, &info);
@@ -270,7 +270,8 @@ int main(int argc, char* argv[]) {
                "\t-numthreads X: number of worker threads, each with its own plan (default 1)\n"
                "\t-gpus X: (extension) spread the worker threads over X CUDA devices (default 1)\n"
                "\t-c2c: (extension) reproduce the reference's C2C branch (what VkResample runs when the upscaled width\n"
-               "\t      exceeds its shared-memory limit, e.g. > 6144 on NVIDIA); default is R2C/C2R at every size\n");
+               "\t      exceeds its shared-memory limit, e.g. > 6144 on NVIDIA); default is R2C/C2R at every size\n"
+               "\t-fast: (extension) approximate divisions / square root in the sharpen (B2R_FLAG_FAST_SHARPEN)\n");
         return 0;
     }
     if (find_flag(argv, argv + argc, "-pngcopy")) {  // diagnostic: decode + re-encode (codec self-test, no GPU)
@@ -299,6 +300,7 @@ int main(int argc, char* argv[]) {
         need("-s", "%f", &cfg.sharpen) || need("-u", "%f", &cfg.upscale) || need("-gpus", "%u", &cfg.gpus))
         return 1;
     cfg.c2c = find_flag(argv, argv + argc, "-c2c") ? 1u : 0u;
+    cfg.fast = find_flag(argv, argv + argc, "-fast") ? 1u : 0u;
     if (find_flag(argv, argv + argc, "-ifolder")) {  // batch mode, VkResample.cpp:1893-1957
         cfg.upload_files = 1;
         cfg.ifolder = flag_value(argv, argv + argc, "-ifolder");
