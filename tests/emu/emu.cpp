@@ -287,7 +287,7 @@ int b2r_emu_frame(int w, int h, float upscale, int precision, float sharpen_cons
         if (use_static) {
 #define X(N, PPB, T, ...) \
             if (!done && g.w == N) { using P = StaticFft<N, T, __VA_ARGS__>; host_fft_of<P>(&hf); emu_r2c<P, PPB>(c, P{}, hf); done = true; used |= 1; }
-            B2R_STATIC_ROWS(X)
+            B2R_STATIC_R2C_ROWS(X)
 #undef X
         }
         if (!done) {
@@ -318,7 +318,7 @@ int b2r_emu_frame(int w, int h, float upscale, int precision, float sharpen_cons
         if (use_static) {
 #define X(N, PPB, T, ...) \
             if (!done && g.up_w == N) { using P = StaticFft<N, T, __VA_ARGS__>; host_fft_of<P>(&hf); emu_c2r<P, PPB>(c, P{}, hf); done = true; used |= 4; }
-            B2R_STATIC_ROWS(X)
+            B2R_STATIC_C2R_ROWS(X)
 #undef X
         }
         if (!done) {

@@ -177,35 +177,39 @@ int build(b2r_plan* p) {
     // fp64: nothing is built ahead of time -- the whole kernel set is compiled at plan time; the static
     // table still supplies the schedule for the sizes it lists
     const bool force_dyn = env_int("B2R_FORCE_DYNAMIC", 0) != 0 || dbl;
+    // tuning aid: B2R_FORCE_JIT=1 compiles the schedules at plan time even for sizes with an ahead-of-time
+    // build, so that B2R_TUNE_* (thread counts, tile widths, radix orders) can be swept without rebuilding
+    const bool force_jit = !force_dyn && env_int("B2R_FORCE_JIT", 0) != 0;
+    const bool seed = dbl || force_jit;        // take the static table's schedule as the starting point
     const size_t cb = g.cplx_bytes();
     RowImpl st_r2c, st_c2r; ColImpl st_cols;
     const bool has_r2c = find_static_r2c(g.w, &st_r2c), has_c2r = find_static_c2r(g.up_w, &st_c2r);
     const bool has_cols = find_static_cols(g.h, g.up_h, &st_cols);
 
     // ---- resolve kernels: static schedule when the size was instantiated, else dynamic
-    if (!force_dyn && find_static_r2c(g.w, &p->k_r2c)) {
+    if (!force_dyn && !force_jit && find_static_r2c(g.w, &p->k_r2c)) {
         build_fft(g.w, p->k_r2c.sched.radices, p->k_r2c.sched.nst, p->k_r2c.sched.threads, &p->fw);
     } else {
-        if (dbl && has_r2c) build_fft(g.w, st_r2c.sched.radices, st_r2c.sched.nst, st_r2c.sched.threads, &p->fw);
+        if (seed && has_r2c) build_fft(g.w, st_r2c.sched.radices, st_r2c.sched.nst, st_r2c.sched.threads, &p->fw);
         else if (!schedule_fft(g.w, &p->fw, &err)) return fail(B2R_ERR_UNSUPPORTED, "%s", err.c_str());
         get_dynamic_r2c(&p->k_r2c);
         sched_from(p->fw, &p->k_r2c.sched);
         p->k_r2c.smem = (size_t)p->k_r2c.ppb * smem_padded_len(g.w) * sizeof(float2);
     }
-    if (!force_dyn && find_static_c2r(g.up_w, &p->k_c2r)) {
+    if (!force_dyn && !force_jit && find_static_c2r(g.up_w, &p->k_c2r)) {
         build_fft(g.up_w, p->k_c2r.sched.radices, p->k_c2r.sched.nst, p->k_c2r.sched.threads, &p->fuw);
     } else {
-        if (dbl && has_c2r) build_fft(g.up_w, st_c2r.sched.radices, st_c2r.sched.nst, st_c2r.sched.threads, &p->fuw);
+        if (seed && has_c2r) build_fft(g.up_w, st_c2r.sched.radices, st_c2r.sched.nst, st_c2r.sched.threads, &p->fuw);
         else if (!schedule_fft(g.up_w, &p->fuw, &err)) return fail(B2R_ERR_UNSUPPORTED, "%s", err.c_str());
         get_dynamic_c2r(&p->k_c2r);
         sched_from(p->fuw, &p->k_c2r.sched);
         p->k_c2r.smem = (size_t)p->k_c2r.ppb * smem_padded_len(g.up_w) * sizeof(float2);
     }
-    if (!force_dyn && find_static_cols(g.h, g.up_h, &p->k_cols)) {
+    if (!force_dyn && !force_jit && find_static_cols(g.h, g.up_h, &p->k_cols)) {
         build_fft(g.h, p->k_cols.fwd.radices, p->k_cols.fwd.nst, p->k_cols.fwd.threads, &p->fh);
         build_fft(g.up_h, p->k_cols.inv.radices, p->k_cols.inv.nst, p->k_cols.inv.threads, &p->fuh);
     } else {
-        if (dbl && has_cols) {
+        if (seed && has_cols) {
             build_fft(g.h, st_cols.fwd.radices, st_cols.fwd.nst, st_cols.fwd.threads, &p->fh);
             build_fft(g.up_h, st_cols.inv.radices, st_cols.inv.nst, st_cols.inv.threads, &p->fuh);
         } else {
@@ -249,11 +253,50 @@ int build(b2r_plan* p) {
                 while (4 * t2 > 640) t2 = (((t2 + 1) / 2) + 7) & ~7;
                 rq.cc = 4; rq.h.threads = rq.uh.threads = t2;
             }
+            // row kernels (sweeps on B200, scripts/jit_sweep.py): K1 with one row pair per CTA from W = 960 up;
+            // K7 with two butterflies per thread from upW = 2560 up while a thread holds <= 16 values
+            if (!dbl && !force_jit) {
+                if (rq.want_r2c && g.w >= 960) rq.ppb_w = 1;
+                if (rq.want_c2r && g.up_w >= 2560) {
+                    int rmax = 0;
+                    for (int i = 0; i < rq.uw.nst; ++i) rmax = std::max(rmax, rq.uw.radices[i]);
+                    const int t2 = (((rq.uw.threads + 1) / 2) + 7) & ~7;
+                    int rmin = 99;
+                    for (int i = 0; i < rq.uw.nst; ++i) rmin = std::min(rmin, rq.uw.radices[i]);
+                    if (rmax <= 16 && rmin >= 8 && t2 >= 96) rq.uw.threads = t2;
+                }
+            }
+            if (force_jit) {
+                if (has_cols) rq.cc = st_cols.cc;
+                auto tune = [&](Schedule& sc, const char* axis) {   // B2R_TUNE_T<axis>=threads  B2R_TUNE_R<axis>=r0,r1,...
+                    const std::string a(axis);
+                    sc.threads = env_int(("B2R_TUNE_T" + a).c_str(), sc.threads);
+                    if (const char* e = getenv(("B2R_TUNE_R" + a).c_str())) {
+                        int prod = 1, n = 0, rad[kMaxStages];
+                        for (const char* q = e; *q && n < kMaxStages; ) {
+                            rad[n] = atoi(q); prod *= rad[n] > 0 ? rad[n] : 0; ++n;
+                            while (*q && *q != ',') ++q;
+                            if (*q == ',') ++q;
+                        }
+                        if (prod == sc.n) { sc.nst = n; for (int i = 0; i < n; ++i) sc.radices[i] = rad[i]; }
+                    }
+                };
+                tune(rq.w, "W"); tune(rq.h, "H"); tune(rq.uh, "UH"); tune(rq.uw, "UW");
+                rq.uh.threads = rq.h.threads = std::max(rq.h.threads, rq.uh.threads);
+                rq.cc = env_int("B2R_TUNE_CC", rq.cc);
+                rq.ppb_w = env_int("B2R_TUNE_PPBW", has_r2c ? st_r2c.ppb : 0);
+            }
             RowImpl jr, jc; ColImpl jcol;
             if (jit_build(rq, &p->jit, &jr, &jcol, &jc, &why)) {
                 if (rq.want_r2c) p->k_r2c = jr;
                 if (rq.want_cols) p->k_cols = jcol;
                 if (rq.want_c2r) p->k_c2r = jc;
+                if (force_jit) {   // twiddle tables follow the (possibly re-ordered) radix lists
+                    build_fft(g.w, rq.w.radices, rq.w.nst, rq.w.threads, &p->fw);
+                    build_fft(g.h, rq.h.radices, rq.h.nst, rq.h.threads, &p->fh);
+                    build_fft(g.up_h, rq.uh.radices, rq.uh.nst, rq.uh.threads, &p->fuh);
+                    build_fft(g.up_w, rq.uw.radices, rq.uw.nst, rq.uw.threads, &p->fuw);
+                }
             } else {
                 p->jit_note = why;
             }

@@ -43,6 +43,7 @@ struct Api {
     CUresult (*cuModuleUnload)(CUmodule) = nullptr;
     CUresult (*cuModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
     CUresult (*cuFuncSetAttribute)(CUfunction, int, int) = nullptr;
+    CUresult (*cuFuncGetAttribute)(int*, int, CUfunction) = nullptr;   // optional (B2R_JIT_VERBOSE)
     CUresult (*cuLaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream,
                                void**, void**) = nullptr;
     CUresult (*cuOccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t) = nullptr;
@@ -78,6 +79,7 @@ Api& api() {
         for (const auto& c : cands)
             if ((rtc = dlopen(c.c_str(), RTLD_NOW))) break;
         if (!rtc) { a.why = "libnvrtc.so.12 not found (set B2R_NVRTC or CUDA_HOME)"; return; }
+        sym(cu, "cuFuncGetAttribute", &a.cuFuncGetAttribute);
         bool ok = sym(cu, "cuModuleLoadData", &a.cuModuleLoadData) && sym(cu, "cuModuleUnload", &a.cuModuleUnload) &&
                   sym(cu, "cuModuleGetFunction", &a.cuModuleGetFunction) && sym(cu, "cuFuncSetAttribute", &a.cuFuncSetAttribute) &&
                   sym(cu, "cuLaunchKernel", &a.cuLaunchKernel) &&
@@ -237,7 +239,7 @@ bool jit_build(const JitRequest& rq, JitModule** out_mod, RowImpl* r2c, ColImpl*
     const size_t cb = dbl ? 16 : 8;   // bytes of one complex workspace element
     const char* tin = rq.precision == 2 ? "__half" : (dbl ? "double" : "float");
     std::vector<std::string> names;   // name expressions, in the order r2c, cols, c2r, c2c
-    const int ppb_w = std::max(1, std::min(8, 256 / rq.w.threads));
+    const int ppb_w = rq.ppb_w > 0 ? rq.ppb_w : std::max(1, std::min(8, 256 / rq.w.threads));
     const int ppb_uw = std::max(1, std::min(8, 256 / rq.uw.threads));
     if (rq.want_r2c) {
         std::ostringstream n;
@@ -343,9 +345,16 @@ bool jit_build(const JitRequest& rq, JitModule** out_mod, RowImpl* r2c, ColImpl*
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     bool ok = true;
+    auto report = [&](const char* what, CUfunction f) {   // B2R_JIT_VERBOSE=1: registers per thread of each kernel
+        const char* e = getenv("B2R_JIT_VERBOSE");
+        int regs = 0;
+        if (e && atoi(e) != 0 && f && a.cuFuncGetAttribute && a.cuFuncGetAttribute(&regs, 4 /* NUM_REGS */, f) == 0)
+            fprintf(stderr, "[b2r jit] %s: %d registers/thread\n", what, regs);
+    };
     if (rq.want_r2c) {
         m->r2c.m = m; m->r2c.threads = rq.w.threads; m->r2c.ppb = ppb_w; m->r2c.dbl = dbl;
         ok = ok && get(&m->r2c.fn);
+        report(names[idx - 1].c_str(), m->r2c.fn);
         *r2c = RowImpl{};
         r2c->name = "r2c_rows<jit>"; r2c->is_static = true; r2c->is_jit = true; r2c->sched = rq.w; r2c->ppb = ppb_w;
         r2c->smem = (size_t)ppb_w * smem_padded_len(rq.w.n) * cb;
@@ -354,6 +363,7 @@ bool jit_build(const JitRequest& rq, JitModule** out_mod, RowImpl* r2c, ColImpl*
     if (rq.want_cols) {
         m->cols.m = m; m->cols.threads = rq.uh.threads; m->cols.cc = rq.cc; m->cols.dbl = dbl;
         ok = ok && get(&m->cols.fn);
+        report(names[idx - 1].c_str(), m->cols.fn);
         *cols = ColImpl{};
         cols->name = "cols<jit>"; cols->is_static = true; cols->is_jit = true; cols->fwd = rq.h; cols->inv = rq.uh; cols->cc = rq.cc;
         cols->smem = (size_t)smem_padded_len(rq.uh.n * rq.cc) * cb;
@@ -362,6 +372,7 @@ bool jit_build(const JitRequest& rq, JitModule** out_mod, RowImpl* r2c, ColImpl*
     if (rq.want_c2r) {
         m->c2r.m = m; m->c2r.threads = rq.uw.threads; m->c2r.ppb = ppb_uw; m->c2r.bulk = true; m->c2r.sms = sms; m->c2r.dbl = dbl;
         ok = ok && get(&m->c2r.fn);
+        report(names[idx - 1].c_str(), m->c2r.fn);
         if (rq.c2c) ok = ok && get(&m->c2r.fn_c2c);
         *c2r = RowImpl{};
         c2r->name = "c2r_rows_bulk<jit>"; c2r->is_static = true; c2r->is_jit = true; c2r->sched = rq.uw; c2r->ppb = 1;

@@ -18,6 +18,7 @@ struct JitRequest {
     bool up2 = false;          // upW == 2*W: static first-stage operand pattern in the C2R kernel
     bool c2c = false;          // also build k_c2c_rows (B2R_FLAG_C2C_PARITY)
     int cc = 4;                // column tile width
+    int ppb_w = 0;             // row pairs per CTA of the R2C kernel (0: 256 threads' worth)
     int nx = 0;                // W/2 + 1
     bool cache_only = false;   // only use a cubin already in the disk cache, never compile
 };

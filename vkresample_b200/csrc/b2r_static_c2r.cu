@@ -106,7 +106,7 @@ template <class P, int PPB> void fill(RowImpl* o, const char* name) {
 bool find_static_c2r(int n, RowImpl* out) {
 #define X(N, PPB, T, ...) \
     if (n == N) { fill<StaticFft<N, T, __VA_ARGS__>, PPB>(out, "c2r_rows<" #N ">"); return true; }
-    B2R_STATIC_ROWS(X)
+    B2R_STATIC_C2R_ROWS(X)
 #undef X
     return false;
 }

@@ -34,7 +34,7 @@ template <class P, int PPB> void fill(RowImpl* o, const char* name) {
 bool find_static_r2c(int n, RowImpl* out) {
 #define X(N, PPB, T, ...) \
     if (n == N) { fill<StaticFft<N, T, __VA_ARGS__>, PPB>(out, "r2c_rows<" #N ">"); return true; }
-    B2R_STATIC_ROWS(X)
+    B2R_STATIC_R2C_ROWS(X)
 #undef X
     return false;
 }

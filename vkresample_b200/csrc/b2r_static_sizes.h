@@ -7,28 +7,52 @@
 // plan time (b2r_jit.cpp, NVRTC) or, without NVRTC, runs through the dynamic kernels (b2r_dynamic.cu) at
 // about half the speed -- add a line here and rebuild to promote a size.
 //
-// Row list:  X(N, PPB, T, radices...)   N-point complex transform of one row pair, T threads per
-//            pair, PPB pairs per CTA.  Used for both K1 (N = W) and K7 (N = upW).
+// Row lists: X(N, PPB, T, radices...)   N-point complex transform of one row pair, T threads per
+//            pair, PPB pairs per CTA; one list for K1 (N = W), one for K7 (N = upW).
 // Column list: X(H, UPH, CC, FWD, INV)  fused column kernel, CC columns per CTA, FWD / INV are
 //            StaticFft aliases with the same thread count.
 #pragma once
 
 #include "b2r_fft.cuh"
 
-#define B2R_STATIC_ROWS(X)              \
+// Thread counts / pairs per CTA come from sweeps on B200 through the plan-time JIT (scripts/jit_sweep.py:
+// B2R_FORCE_JIT=1 + B2R_TUNE_*, no rebuild per variant): K1 is fastest with one row pair per CTA and one
+// butterfly per thread in the widest stage; K7 (persistent, bulk-copy fed) is fastest with two butterflies
+// per thread once N >= 2560 (4096: 39.1 -> 35.6 us, 3840: 42.7 -> 37.0 us, 5120: 92.3 -> 82.3 us).
+#define B2R_STATIC_R2C_ROWS(X)          \
+    X(256, 8, 16, 16, 16)               \
+    X(512, 4, 32, 16, 8, 4)             \
+    X(1024, 4, 64, 16, 16, 4)           \
+    X(2048, 1, 128, 16, 16, 8)          \
+    X(4096, 1, 256, 16, 16, 16)         \
+    X(1920, 1, 128, 16, 15, 8)          \
+    X(3840, 1, 256, 16, 16, 15)         \
+    X(640, 4, 64, 16, 8, 5)             \
+    X(960, 1, 64, 16, 15, 4)            \
+    X(1280, 1, 96, 16, 16, 5)           \
+    X(2560, 1, 160, 16, 16, 10)
+
+#define B2R_STATIC_C2R_ROWS(X)          \
     X(256, 8, 16, 16, 16)               \
     X(512, 4, 32, 16, 8, 4)             \
     X(1024, 4, 64, 16, 16, 4)           \
     X(2048, 2, 128, 16, 16, 8)          \
-    X(4096, 1, 256, 16, 16, 16)         \
+    X(4096, 1, 128, 16, 16, 16)         \
     X(1920, 2, 128, 16, 15, 8)          \
-    X(3840, 1, 256, 16, 16, 15)         \
+    X(3840, 1, 128, 16, 16, 15)         \
     X(7680, 1, 480, 24, 20, 16)         \
     X(640, 4, 64, 16, 8, 5)             \
     X(960, 4, 64, 16, 15, 4)            \
     X(1280, 2, 96, 16, 16, 5)           \
-    X(2560, 1, 256, 16, 16, 10)         \
-    X(5120, 1, 320, 20, 16, 16)         \
+    X(2560, 1, 128, 16, 16, 10)         \
+    X(5120, 1, 160, 20, 16, 16)         \
+    X(4320, 1, 288, 18, 16, 15)
+
+// every row schedule once (tests of the bare transforms)
+#define B2R_STATIC_ROWS(X)              \
+    B2R_STATIC_R2C_ROWS(X)              \
+    X(7680, 1, 480, 24, 20, 16)         \
+    X(5120, 1, 160, 20, 16, 16)         \
     X(4320, 1, 288, 18, 16, 15)
 
 namespace b2r {
@@ -36,7 +60,7 @@ using ColF128 = StaticFft<128, 16, 16, 8>;
 using ColI256 = StaticFft<256, 16, 16, 16>;
 using ColF512 = StaticFft<512, 64, 16, 8, 4>;
 using ColI1024 = StaticFft<1024, 64, 16, 16, 4>;
-using ColF1024 = StaticFft<1024, 128, 16, 16, 4>;
+using ColF1024 = StaticFft<1024, 128, 16, 4, 16>;   // radix order from the sweep: 42.7 -> 41.7 us
 using ColI2048 = StaticFft<2048, 128, 16, 16, 8>;
 // 8-column tile (64-byte rows), two butterflies per thread: 47.1 us against 54.1 us for <.., 180, ..> x 4 columns
 using ColF1080 = StaticFft<1080, 90, 15, 12, 6>;
