@@ -243,7 +243,7 @@ def run_b200(args):
     # ---- the same device-resident measurement with B2R_FLAG_FAST_SHARPEN (approximate divisions / sqrt in the
     # sharpen, within 2e-6 of the default); reported beside the headline, never instead of it
     fast = None
-    if not args.fast_sharpen:
+    if not args.fast_sharpen and not args.no_fast_leg:
         with vb.Plan(w, h, up, prec, s, device=local, flags=vb.FLAG_FAST_SHARPEN) as pf:
             pf.set_lanes(args.lanes)
             f_steps = max(1, min(args.steps, 10))
@@ -394,6 +394,7 @@ def main():
     ap.add_argument("--lanes", type=int, default=3,
                     help="concurrent frames in flight per GPU (like the reference's -numthreads on one device)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fast-leg", action="store_true", help="skip the extra B2R_FLAG_FAST_SHARPEN measurement (profiling runs)")
     ap.add_argument("--fast-sharpen", action="store_true",
                     help="create the plan with B2R_FLAG_FAST_SHARPEN (not the default; recorded in config)")
     args = ap.parse_args()

@@ -40,7 +40,7 @@
     X(4096, 1, 128, 16, 16, 16)         \
     X(1920, 2, 128, 16, 15, 8)          \
     X(3840, 1, 128, 16, 16, 15)         \
-    X(7680, 1, 480, 24, 20, 16)         \
+    X(7680, 1, 384, 16, 20, 24)         \
     X(640, 4, 64, 16, 8, 5)             \
     X(960, 4, 64, 16, 15, 4)            \
     X(1280, 2, 96, 16, 16, 5)           \
@@ -51,7 +51,7 @@
 // every row schedule once (tests of the bare transforms)
 #define B2R_STATIC_ROWS(X)              \
     B2R_STATIC_R2C_ROWS(X)              \
-    X(7680, 1, 480, 24, 20, 16)         \
+    X(7680, 1, 384, 16, 20, 24)         \
     X(5120, 1, 160, 20, 16, 16)         \
     X(4320, 1, 288, 18, 16, 15)
 
@@ -64,7 +64,7 @@ using ColF1024 = StaticFft<1024, 128, 16, 4, 16>;   // radix order from the swee
 using ColI2048 = StaticFft<2048, 128, 16, 16, 8>;
 // 8-column tile (64-byte rows), two butterflies per thread: 47.1 us against 54.1 us for <.., 180, ..> x 4 columns
 using ColF1080 = StaticFft<1080, 90, 15, 12, 6>;
-using ColI2160 = StaticFft<2160, 90, 15, 12, 12>;
+using ColI2160 = StaticFft<2160, 90, 12, 12, 15>;
 using ColF1080n = StaticFft<1080, 180, 15, 12, 6>;
 using ColI2160n = StaticFft<2160, 180, 15, 12, 12>;
 using ColF360 = StaticFft<360, 48, 15, 8, 3>;
@@ -77,8 +77,8 @@ using ColF1440 = StaticFft<1440, 240, 16, 15, 6>;
 using ColI2880 = StaticFft<2880, 240, 16, 15, 12>;
 // 4-column tile (32 B = one DRAM sector per spectrum row), two butterflies per thread: 193 us against
 // 312 us for <4320, 288, ...> with 2 columns per CTA (one CTA per SM either way)
-using ColF2160 = StaticFft<2160, 144, 15, 16, 9>;
-using ColI4320 = StaticFft<4320, 144, 18, 16, 15>;
+using ColF2160 = StaticFft<2160, 144, 16, 9, 15>;    // radix-16 stage first: 199 -> 178 us (jit_sweep)
+using ColI4320 = StaticFft<4320, 144, 16, 15, 18>;
 using ColF1024h = StaticFft<1024, 64, 16, 16, 4>;
 using ColI2048h = StaticFft<2048, 64, 16, 16, 8>;
 using ColF1440h = StaticFft<1440, 96, 16, 15, 6>;
