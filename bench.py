@@ -158,7 +158,7 @@ def run_reference(args):
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -375,7 +375,7 @@ def run_b200(args):
             line["fast_sharpen"] = fast
         if cpu:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line))
+        emit(line)
     plan.close()
     if dist is not None:
         dist.destroy_process_group()
@@ -399,9 +399,26 @@ def main():
                     help="create the plan with B2R_FLAG_FAST_SHARPEN (not the default; recorded in config)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    # stdout carries exactly ONE JSON line: everything libraries print to fd 1 while we run (e.g. NCCL's
+    # "NCCL version ..." banner under torchrun) is sent to stderr, the result line goes to the real stdout
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         return run_reference(args)
     return run_b200(args)
+
+
+_RESULT_FD = None
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
 
 
 if __name__ == "__main__":
