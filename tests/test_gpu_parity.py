@@ -367,6 +367,32 @@ def test_plan_time_jit(w, h, up, prec, tmp_path, monkeypatch):
     assert np.abs(out.astype(np.float64) - ref.astype(np.float64)).max() <= tol
 
 
+def test_forced_jit_with_tuning_overrides(tmp_path, monkeypatch):
+    """B2R_FORCE_JIT + B2R_TUNE_* (scripts/jit_sweep.py): a size with an ahead-of-time build compiled at plan
+    time with other thread counts, tile width and radix orders must give the same frame (same arithmetic up to
+    the summation order of the butterflies) and keep every parity bar"""
+    w, h = 1024, 512
+    x = vo.synthetic_frame("noise", w, h).astype(np.float32)
+    with vb.Plan(w, h, 2.0, 0, 0.2) as p0:
+        assert p0.info.jit_kernels == 0
+        ref = p0.upscale(x).copy()
+    monkeypatch.setenv("B2R_CACHE_DIR", str(tmp_path))
+    monkeypatch.setenv("B2R_FORCE_JIT", "1")
+    for env in ({}, {"B2R_TUNE_TW": "32", "B2R_TUNE_PPBW": "2", "B2R_TUNE_TUW": "64"},
+                {"B2R_TUNE_RW": "4,16,16", "B2R_TUNE_RUH": "4,16,16", "B2R_TUNE_CC": "8", "B2R_TUNE_RUW": "8,16,16"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        _check(w, h, 2.0, 0, 0.2, "noise", expect_jit=7)
+        with vb.Plan(w, h, 2.0, 0, 0.2) as p1:
+            out = p1.upscale(x)
+            sched = p1.radix_schedule()
+        if "B2R_TUNE_RW" in env:
+            assert sched["W"] == [4, 16, 16] and sched["upW"] == [8, 16, 16] and sched["upH"] == [4, 16, 16], sched
+        assert np.abs(out.astype(np.float64) - ref.astype(np.float64)).max() <= 2e-4
+        for k in env:
+            monkeypatch.delenv(k)
+
+
 @pytest.mark.parametrize("w,h,up", [(256, 128, 2.0), (2048, 1024, 2.0), (600, 360, 1.5), (1920, 1080, 2.0)])
 def test_double_precision(w, h, up):
     """-p 1 (VkResample.cpp:1860-1866): double storage and arithmetic.  The whole kernel set is compiled
