@@ -52,15 +52,6 @@ cudaError_t run_c2c(cudaStream_t s, const C2rArgs& a, int threads, size_t smem, 
         k_c2c_rows<DynFft, float, kDynPPB><<<grid, block, smem, s>>>(a.spec, a.nyq, (float*)a.pre, a.tw, DynFft{a.dfd}, a.dm, rows, a.scale);
     return cudaGetLastError();
 }
-template <int CC> cudaError_t prep_cols(size_t smem, const void*) {
-    if (smem <= 48 * 1024) return cudaSuccess;
-    return cudaFuncSetAttribute(k_cols<DynFft, DynFft, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-}
-template <int CC> cudaError_t run_cols(cudaStream_t s, const ColsArgs& a, int threads, size_t smem, const void*) {
-    dim3 block(threads * CC), grid((a.dm.nx + CC - 1) / CC, 3);
-    k_cols<DynFft, DynFft, CC><<<grid, block, smem, s>>>(a.in, a.out, a.tw_f, a.tw_i, DynFft{a.dfd_f}, DynFft{a.dfd_i}, a.dm, a.scale, a.nyq);
-    return cudaGetLastError();
-}
 }  // namespace
 
 void get_dynamic_r2c(RowImpl* o) {
@@ -73,11 +64,9 @@ void get_dynamic_c2r(RowImpl* o) {
     o->c2c = &run_c2c; o->prepare_c2c = &prep_c2c; o->ppb_c2c = kDynPPB;
 }
 void get_dynamic_cols(int cc, ColImpl* o) {
-    *o = ColImpl{};
-    o->name = "cols<dynamic>"; o->cc = cc;
-    if (cc == 8) { o->prepare = &prep_cols<8>; o->launch = &run_cols<8>; }
-    else if (cc == 4) { o->prepare = &prep_cols<4>; o->launch = &run_cols<4>; }
-    else if (cc == 1) { o->prepare = &prep_cols<1>; o->launch = &run_cols<1>; }
-    else { o->cc = 2; o->prepare = &prep_cols<2>; o->launch = &run_cols<2>; }
+    if (cc == 8) get_dynamic_cols_cc8(o);
+    else if (cc == 4) get_dynamic_cols_cc4(o);
+    else if (cc == 1) get_dynamic_cols_cc1(o);
+    else get_dynamic_cols_cc2(o);
 }
 }  // namespace b2r

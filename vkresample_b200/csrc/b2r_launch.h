@@ -67,11 +67,19 @@ struct ColImpl {       // fused column kernel resolved for one (H, upH) pair
 // static registries: return false when the size was not instantiated at build time
 bool find_static_r2c(int n, RowImpl* out);
 bool find_static_c2r(int n, RowImpl* out);
+bool find_static_c2r_part0(int n, RowImpl* out);   // b2r_static_c2r.cu, one translation unit per part
+bool find_static_c2r_part1(int n, RowImpl* out);
+bool find_static_c2r_part2(int n, RowImpl* out);
+bool find_static_c2r_part3(int n, RowImpl* out);
 bool find_static_cols(int h, int up_h, ColImpl* out);
 // dynamic fallbacks (always succeed for schedulable sizes); cc in {2,4,8}
 void get_dynamic_r2c(RowImpl* out);
 void get_dynamic_c2r(RowImpl* out);
 void get_dynamic_cols(int cc, ColImpl* out);
+void get_dynamic_cols_cc1(ColImpl* out);           // b2r_dynamic_cols.cu, one translation unit per tile width
+void get_dynamic_cols_cc2(ColImpl* out);
+void get_dynamic_cols_cc4(ColImpl* out);
+void get_dynamic_cols_cc8(ColImpl* out);
 
 cudaError_t launch_sharpen_kernel(cudaStream_t s, const SharpenArgs& a);
 cudaError_t launch_u8_to_planar(cudaStream_t s, const unsigned char* src, void* dst, const FrameDims& dm, int precision);

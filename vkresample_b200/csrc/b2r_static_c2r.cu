@@ -103,11 +103,23 @@ template <class P, int PPB> void fill(RowImpl* o, const char* name) {
 }
 }  // namespace
 
-bool find_static_c2r(int n, RowImpl* out) {
+// This file is compiled once per part of the size list (-DB2R_C2R_PART=0..3, see the Makefile).
+#ifndef B2R_C2R_PART
+#error "compile with -DB2R_C2R_PART=0..3"
+#endif
+#define B2R_CAT2(a, b) a##b
+#define B2R_CAT(a, b) B2R_CAT2(a, b)
+bool B2R_CAT(find_static_c2r_part, B2R_C2R_PART)(int n, RowImpl* out) {
 #define X(N, PPB, T, ...) \
     if (n == N) { fill<StaticFft<N, T, __VA_ARGS__>, PPB>(out, "c2r_rows<" #N ">"); return true; }
-    B2R_STATIC_C2R_ROWS(X)
+    B2R_CAT(B2R_STATIC_C2R_ROWS_, B2R_C2R_PART)(X)
 #undef X
     return false;
 }
+#if B2R_C2R_PART == 0
+bool find_static_c2r(int n, RowImpl* out) {
+    return find_static_c2r_part0(n, out) || find_static_c2r_part1(n, out) || find_static_c2r_part2(n, out) ||
+           find_static_c2r_part3(n, out);
+}
+#endif
 }  // namespace b2r

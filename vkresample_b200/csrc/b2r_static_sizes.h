@@ -32,21 +32,30 @@
     X(1280, 1, 96, 16, 16, 5)           \
     X(2560, 1, 160, 16, 16, 10)
 
-#define B2R_STATIC_C2R_ROWS(X)          \
+// (four parts: b2r_static_c2r.cu is compiled once per part so that the build uses more cores)
+#define B2R_STATIC_C2R_ROWS_0(X)        \
     X(256, 8, 16, 16, 16)               \
     X(512, 4, 32, 16, 8, 4)             \
     X(1024, 4, 64, 16, 16, 4)           \
-    X(2048, 2, 128, 16, 16, 8)          \
+    X(2048, 2, 128, 16, 16, 8)
+#define B2R_STATIC_C2R_ROWS_1(X)        \
     X(4096, 1, 128, 16, 16, 16)         \
     X(1920, 2, 128, 16, 15, 8)          \
-    X(3840, 1, 128, 16, 16, 15)         \
+    X(3840, 1, 128, 16, 16, 15)
+#define B2R_STATIC_C2R_ROWS_2(X)        \
     X(7680, 1, 384, 16, 20, 24)         \
     X(640, 4, 64, 16, 8, 5)             \
     X(960, 4, 64, 16, 15, 4)            \
-    X(1280, 2, 96, 16, 16, 5)           \
+    X(1280, 2, 96, 16, 16, 5)
+#define B2R_STATIC_C2R_ROWS_3(X)        \
     X(2560, 1, 128, 16, 16, 10)         \
     X(5120, 1, 160, 20, 16, 16)         \
     X(4320, 1, 288, 18, 16, 15)
+#define B2R_STATIC_C2R_ROWS(X)          \
+    B2R_STATIC_C2R_ROWS_0(X)            \
+    B2R_STATIC_C2R_ROWS_1(X)            \
+    B2R_STATIC_C2R_ROWS_2(X)            \
+    B2R_STATIC_C2R_ROWS_3(X)
 
 // every row schedule once (tests of the bare transforms)
 #define B2R_STATIC_ROWS(X)              \
