@@ -425,3 +425,16 @@ def test_double_precision_u8_api():
     d = np.abs(got.astype(np.int16) - ref.astype(np.int16))
     d = np.minimum(d, 256 - d)
     assert d.max() <= 1 and (d == 0).mean() > 0.9999
+
+
+def test_random_sizes_factors_precisions(tmp_path):
+    """a seeded slice of scripts/fuzz_parity.py: random 2^a 3^b 5^c 7^d sizes, factors 1..4, all three
+    precisions, through whatever kernels the plan resolves to (ahead-of-time or plan-time JIT)"""
+    import subprocess, sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, B2R_CACHE_DIR=str(tmp_path))
+    r = subprocess.run([sys.executable, os.path.join(root, "scripts", "fuzz_parity.py"), "10", "5"], env=env,
+                       capture_output=True, text=True, timeout=900, cwd=root)
+    print(r.stdout[-3000:])
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1000:]
+    assert "10 cases, 0 failures" in r.stdout
