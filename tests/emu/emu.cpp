@@ -217,6 +217,18 @@ static void emu_sharpen(const FrameDims dm, int precision, const void* pre, void
     });
 }
 
+template <class P> static int emu_fft_static(int n, int dir, const float* in, float* out) {
+    HostFft hf;
+    Dim3 grid, block;
+    host_fft_of<P>(&hf); block.x = P::kT;
+    const float2* tw = hf.twiddles.data();
+    b2r_emu::launch(grid, block, smem_padded_len(n) * sizeof(float2), [&] {
+        if (dir < 0) k_fft_test<-1>((const float2*)in, (float2*)out, tw, P{});
+        else k_fft_test<+1>((const float2*)in, (float2*)out, tw, P{});
+    });
+    return 1;
+}
+
 extern "C" {
 
 void b2r_emu_set_c2r_bulk(int on) { g_c2r_bulk = on; }
@@ -232,25 +244,22 @@ int b2r_emu_schedule(int n, int* radices, int* threads) {
     return hf.desc.nstages;
 }
 
-// use_static != 0: run the ahead-of-time schedule for n if one exists (returns 1 if it did)
+// use_static != 0: run an ahead-of-time schedule for n if one exists (returns 1 if it did):
+//   1 = the K1 row list (+ the sizes only K7 has), 2 = the K7 row list (two butterflies per thread for the long
+//   rows), 3 / 4 = the forward / inverse schedules of the fused column kernels
 int b2r_emu_fft(int n, int dir, int use_static, const float* in, float* out) {
     HostFft hf; std::string err;
     Dim3 grid, block;
-    if (use_static) {
-#define X(N, PPB, T, ...)                                                                          \
-        if (n == N) {                                                                              \
-            using P = StaticFft<N, T, __VA_ARGS__>;                                                \
-            host_fft_of<P>(&hf); block.x = T;                                                      \
-            const float2* tw = hf.twiddles.data();                                                 \
-            b2r_emu::launch(grid, block, smem_padded_len(n) * sizeof(float2), [&] {                \
-                if (dir < 0) k_fft_test<-1>((const float2*)in, (float2*)out, tw, P{});             \
-                else k_fft_test<+1>((const float2*)in, (float2*)out, tw, P{});                     \
-            });                                                                                    \
-            return 1;                                                                              \
-        }
-        B2R_STATIC_ROWS(X)
+#define X(N, PPB, T, ...) if (n == N) return emu_fft_static<StaticFft<N, T, __VA_ARGS__>>(n, dir, in, out);
+    if (use_static == 1) { B2R_STATIC_ROWS(X) }
+    if (use_static == 2) { B2R_STATIC_C2R_ROWS(X) }
 #undef X
-    }
+#define X(H, UPH, CC, PF, PI) if (n == H) return emu_fft_static<PF>(n, dir, in, out);
+    if (use_static == 3) { B2R_STATIC_COLS(X) }
+#undef X
+#define X(H, UPH, CC, PF, PI) if (n == UPH) return emu_fft_static<PI>(n, dir, in, out);
+    if (use_static == 4) { B2R_STATIC_COLS(X) }
+#undef X
     if (!schedule_fft(n, &hf, &err)) return -1;
     block.x = (unsigned)hf.desc.threads;
     const float2* tw = hf.twiddles.data();

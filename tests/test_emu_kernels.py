@@ -41,14 +41,23 @@ def test_unschedulable_sizes_rejected():
         assert eu.schedule(n)[0] is None
 
 
-@pytest.mark.parametrize("n", [256, 512, 1024, 2048, 4096, 1920, 3840, 7680, 640, 960, 1280, 2560, 5120, 4320])
-def test_static_schedules(n):
-    """the ahead-of-time schedules of the BASELINE sizes (b2r_static_sizes.h); 7680 = 24*20*16 and
-    4320 = 18*16*15 exercise the nested composite radices (3x(2x4), 4x5, 2x(3x3))"""
-    rng = np.random.default_rng(n)
+_K1_ROWS = [256, 512, 1024, 2048, 4096, 1920, 3840, 7680, 640, 960, 1280, 2560, 5120, 4320]
+_K7_ROWS = [256, 512, 1024, 2048, 4096, 1920, 3840, 7680, 640, 960, 1280, 2560, 5120, 4320]
+_COLS_FWD = [128, 512, 1024, 1080, 2160, 360, 540, 720, 1440]
+_COLS_INV = [256, 1024, 2048, 2160, 4320, 720, 1080, 1440, 2880]
+
+
+@pytest.mark.parametrize("which,n", [(1, n) for n in _K1_ROWS] + [(2, n) for n in _K7_ROWS] +
+                         [(3, n) for n in _COLS_FWD] + [(4, n) for n in _COLS_INV])
+def test_static_schedules(which, n):
+    """every ahead-of-time schedule of b2r_static_sizes.h as a bare transform: the K1 and K7 row lists (K7 runs
+    two butterflies per thread on the long rows; 7680 = 16*20*24 and 4320 = 18*16*15 use the nested composite
+    radices 3x(2x4), 4x5, 2x(3x3)) and the forward / inverse schedules of the fused column kernels (several
+    butterflies per thread for the 8-column and the 4320-point tiles)"""
+    rng = np.random.default_rng(n + which)
     x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
     for d in (-1, 1):
-        out, was_static = eu.fft(x, d, use_static=True)
+        out, was_static = eu.fft(x, d, use_static=which)
         assert was_static == 1
         ref = np.fft.fft(x.astype(np.complex128)) if d < 0 else np.fft.ifft(x.astype(np.complex128)) * n
         assert np.abs(out - ref).max() <= 2e-6 * np.abs(ref).max()
