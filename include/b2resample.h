@@ -62,14 +62,19 @@ extern "C" {
  * any-size kernels on purpose.  B2R_FLAG_JIT is accepted for compatibility and has no effect. */
 #define B2R_FLAG_JIT 8u
 #define B2R_FLAG_NO_JIT 16u
-/* Sharpen divisions / square root through the hardware approximations (rcp.approx + multiply, sqrt.approx:
- * <= 2 ulp each) instead of the correctly rounded IEEE forms the default emulates instruction by
- * instruction.  The reference's GLSL `/` and sqrt() are not correctly rounded either (Vulkan allows 2.5 ulp),
- * so both settings are within the reference's own precision class; the default is bit-identical to the
- * oracle, this one is within 1e-6 (fp32) / one half ulp-step (fp16) of it for 0 <= sharpen <= 0.24 and
- * about 20 % faster in the sharpen kernel.  Ignored for precision 1, for sharpen constants outside
- * [0, 0.24] and for output widths that are not a multiple of 4 (those keep the exact path). */
+/* Sharpen arithmetic.  DEFAULT (since round 2): the tolerance-bound kernels (csrc/b2r_cas.cuh) -- the
+ * reference's formula (VkResample.cpp:909-922) with one quotient instead of two (min(a,b) taken before the
+ * monotone map z/(2-z)), rsqrt / rcp hardware approximations and FMA contraction; within 1e-5 (fp32) /
+ * 1e-2 (fp16) of oracle.sharpen on the identical plane (north_star's bar; measured ~1e-6 / 4e-3), which is
+ * also the precision class of the reference's own GLSL `/` and sqrt() (Vulkan allows 2.5 ulp).  Applies for
+ * 0 <= sharpen <= 0.24, precision 0 / 2 and output widths that are a multiple of 4 (fp32) / 8 (fp16);
+ * everything else runs the exact kernels.
+ * B2R_FLAG_EXACT_SHARPEN: every operation individually rounded in the reference's order -- output
+ * bit-identical to oracle.sharpen (numpy float32 / float16 arithmetic); about 2x the sharpen time.
+ * B2R_FLAG_FAST_SHARPEN: accepted for compatibility (round 1's opt-in); on its own it has no effect any more,
+ * together with B2R_FLAG_EXACT_SHARPEN it selects round 1's approximate-division variant of the exact kernels. */
 #define B2R_FLAG_FAST_SHARPEN 32u
+#define B2R_FLAG_EXACT_SHARPEN 64u
 
 typedef struct b2r_plan b2r_plan;
 

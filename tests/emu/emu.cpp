@@ -369,6 +369,26 @@ int b2r_emu_planar_to_u8(int w, int h, int precision, const void* planar, unsign
     return 0;
 }
 
+// the tolerance-bound sharpen kernels (b2r_cas.cuh), launched as launch_sharpen_fast does (b2r_sharpen.cu)
+int b2r_emu_sharpen_fast(int w, int h, float upscale, int precision, float sharpen_const, float up2_lit, int ry,
+                         int reverse, int block_x, const void* pre, void* out) {
+    Geometry g; std::string err;
+    if (!make_geometry(w, h, upscale, precision, sharpen_const, &g, &err)) return -1;
+    g.up2 = up2_lit;
+    const FrameDims dm = dims_of(g);
+    const int np = (precision == 2 || dm.up_w % 8 == 0) ? 8 : 4;
+    if (dm.up_w % np) return -2;
+    const int vecs = dm.up_w / np, bx = block_x > 0 ? block_x : cas_fast_block(vecs);
+    Dim3 grid, block;
+    block.x = bx; grid.x = (vecs + bx - 1) / bx; grid.y = (dm.up_h + ry - 1) / ry; grid.z = 3;
+    b2r_emu::launch(grid, block, 0, [&] {
+        if (precision == 2) k_sharpen_fast_f16<8>((const __half*)pre, (__half*)out, dm, ry, reverse);
+        else if (np == 8) k_sharpen_fast_f32<2>((const float*)pre, (float*)out, dm, ry, reverse);
+        else k_sharpen_fast_f32<1>((const float*)pre, (float*)out, dm, ry, reverse);
+    });
+    return 0;
+}
+
 // sharpen alone on a caller-provided padded plane buffer (bit-exactness test of K8)
 int b2r_emu_sharpen(int w, int h, float upscale, int precision, float sharpen_const, float up2_lit,
                     const void* pre, void* out) {

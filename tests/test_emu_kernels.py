@@ -152,6 +152,39 @@ def test_sharpen_border_rules(w, h):
     assert np.array_equal(ref.view(np.uint32), out.view(np.uint32))
 
 
+@pytest.mark.parametrize("w,h,prec,ry,rev,bx", [
+    (64, 32, 0, 24, 1, 0), (64, 32, 0, 6, 0, 0), (128, 12, 0, 12, 1, 0), (70, 32, 0, 6, 1, 0), (64, 14, 0, 12, 1, 0),   # 70 -> upW 140: 4-pixel groups
+    (144, 20, 0, 18, 1, 32),                                                                       # ragged last block (36 groups, 32 lanes)
+    (64, 32, 2, 24, 1, 0), (128, 12, 2, 6, 0, 0), (144, 20, 2, 18, 1, 32), (64, 14, 2, 12, 0, 0)])
+def test_fast_sharpen_kernels(w, h, prec, ry, rev, bx):
+    """the tolerance-bound sharpen (b2r_cas.cuh, the default K8): same neighbour rule and formula as the exact
+    kernel, within 1e-5 (fp32) / 1e-2 (fp16) of oracle.sharpen on the identical plane -- noise planes plus
+    saturated / black / constant regions (the m = 0 and m = 1 ends of the quotient)"""
+    plan = vo.make_plan(w, h, 2.0)
+    dt = np.float16 if prec == 2 else np.float32
+    rng = np.random.default_rng(7)
+    pre = np.zeros(3 * plan.pre_plane_stride + plan.up_w + 8, dt)
+    n = plan.up_w * plan.up_h
+    for c in range(3):
+        v = rng.random(n, dtype=np.float32) / 4
+        v[: n // 8] = 0.0                         # black region
+        v[n // 8: n // 4] = 0.25                  # saturated (x up2 = 1)
+        v[n // 4: n // 4 + n // 8] = 0.3          # above 1 after scaling (clamped)
+        v[n // 2: n // 2 + n // 8] = 0.125        # constant mid grey (mn = mx: scale = 1)
+        v[-plan.up_w:] *= -1.0                    # negative values (abs)
+        pre[c * plan.pre_plane_stride: c * plan.pre_plane_stride + n] = v.astype(dt)
+    out = np.zeros((3, plan.up_h, plan.up_w), dt)
+    rc = eu.lib().b2r_emu_sharpen_fast(w, h, 2.0, prec, 0.2, plan.up2, ry, rev, bx, pre.ctypes.data, out.ctypes.data)
+    assert rc == 0
+    ref = vo.sharpen(eu.unpack_pre(pre, plan), plan, 0.2, prec)
+    mask = np.ones(ref.shape, bool)
+    if plan.up_w + 1 > 2 * plan.up_h:
+        mask[:, -1, -1] = False                   # reads the next plane / past the buffer (SURVEY section 7)
+    err = np.abs(out.astype(np.float64) - ref.astype(np.float64))[mask].max()
+    assert np.isfinite(out.astype(np.float64)).all()
+    assert err <= (1e-2 if prec == 2 else 1e-5), err
+
+
 @pytest.mark.parametrize("prec", [0, 2])
 def test_u8_pixel_kernels(prec):
     """GPU forms of the reference's host loops: u8/255 fill (VkResample.cpp:1636-1685) and the

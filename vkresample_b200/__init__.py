@@ -27,7 +27,8 @@ FLAG_NO_SHARPEN_LITERAL_ROUNDING = 2
 FLAG_C2C_PARITY = 4
 FLAG_JIT = 8
 FLAG_NO_JIT = 16
-FLAG_FAST_SHARPEN = 32   # approximate (<= 2 ulp) divisions / sqrt in the sharpen, see b2resample.h
+FLAG_FAST_SHARPEN = 32   # round-1 opt-in, now a no-op on its own (the default sharpen is the tolerance-bound one)
+FLAG_EXACT_SHARPEN = 64  # bit-exact (oracle-identical) sharpen kernels, see b2resample.h
 
 # every symbol include/b2resample.h declares (checked by tests/test_abi.py)
 EXPORTS = [

@@ -119,7 +119,8 @@ namespace {
 
 int launch_sharpen(b2r_plan* p, cudaStream_t s, void* d_out = nullptr, const Lane* ln = nullptr) {
     SharpenArgs a{ln ? ln->d_pre : p->d_pre, d_out ? d_out : (ln ? ln->d_out : p->d_out), p->dm, p->g.precision};
-    a.approx = (p->flags & B2R_FLAG_FAST_SHARPEN) != 0;   // fp32 / fp16 only; the double shader stays IEEE
+    a.exact = (p->flags & B2R_FLAG_EXACT_SHARPEN) != 0;   // default: tolerance-bound kernels (b2r_cas.cuh)
+    a.approx = (p->flags & B2R_FLAG_FAST_SHARPEN) != 0;   // exact kernels only: round-1 approximate-division variant
     if (p->g.precision == 1) CU(jit_launch_sharpen(p->jit, s, a));
     else CU(launch_sharpen_kernel(s, a));
     return B2R_SUCCESS;

@@ -27,7 +27,10 @@ struct C2rArgs {
 };
 struct SharpenArgs {
     const void* pre; void* out; FrameDims dm; int precision;
-    bool approx = false;   // B2R_FLAG_FAST_SHARPEN
+    bool approx = false;   // exact kernels only: the round-1 approximate-division variant (tuning / comparison)
+    bool exact = false;    // B2R_FLAG_EXACT_SHARPEN: bit-exact kernels instead of the tolerance-bound default
+    int ry = 0;            // rows per thread of the fast kernels (0: default)
+    int reverse = -1;      // fast kernels: walk planes / strips against K7's write order (-1: default)
 };
 
 struct Schedule {      // radix list + cooperating threads of one transform
@@ -82,6 +85,7 @@ void get_dynamic_cols_cc4(ColImpl* out);
 void get_dynamic_cols_cc8(ColImpl* out);
 
 cudaError_t launch_sharpen_kernel(cudaStream_t s, const SharpenArgs& a);
+bool sharpen_fast_applies(const SharpenArgs& a);   // true: the tolerance-bound kernels (b2r_cas.cuh) will run
 cudaError_t launch_u8_to_planar(cudaStream_t s, const unsigned char* src, void* dst, const FrameDims& dm, int precision);
 cudaError_t launch_planar_to_u8(cudaStream_t s, const void* src, unsigned char* dst, const FrameDims& dm, int precision);
 

@@ -2,8 +2,45 @@
 #include "b2r_launch.h"
 #include <type_traits>
 
+#include <cstdlib>
+
 namespace b2r {
+namespace {
+int env_or(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return (e && *e) ? atoi(e) : dflt;
+}
+}  // namespace
+
+// Tolerance-bound kernels (b2r_cas.cuh) whenever they apply: 0 <= s <= 0.24 (denominator provably in
+// [0.04, 1]), fp32 / fp16, output width a multiple of 4 (fp32) or 8 (fp16); everything else -- and
+// B2R_FLAG_EXACT_SHARPEN -- runs the bit-exact kernels below.
+bool sharpen_fast_applies(const SharpenArgs& a) {
+    if (a.exact || a.precision == 1) return false;
+    if (!(a.dm.sharpen >= 0.0f && a.dm.sharpen <= kCasFastMaxSharpen)) return false;
+    return a.precision == 2 ? (a.dm.up_w % 8 == 0) : (a.dm.up_w % 4 == 0);
+}
+
+static cudaError_t launch_sharpen_fast(cudaStream_t s, const SharpenArgs& a) {
+    static const int env_ry = env_or("B2R_SHARPEN_RY", 0), env_rev = env_or("B2R_SHARPEN_REVERSE", -1);
+    int ry = a.ry > 0 ? a.ry : (env_ry > 0 ? env_ry : kCasFastRows);
+    ry = (ry + 5) / 6 * 6;
+    const int reverse = a.reverse >= 0 ? a.reverse : (env_rev >= 0 ? env_rev : 1);
+    const int np = (a.precision == 2 || a.dm.up_w % 8 == 0) ? 8 : 4;
+    static const int env_bx = env_or("B2R_SHARPEN_BX", 0);   // tuning aid (a multiple of 32)
+    const int vecs = a.dm.up_w / np, bx = env_bx > 0 ? env_bx : cas_fast_block(vecs);
+    dim3 block(bx), grid((vecs + bx - 1) / bx, (a.dm.up_h + ry - 1) / ry, 3);
+    if (a.precision == 2)
+        k_sharpen_fast_f16<8><<<grid, block, 0, s>>>((const __half*)a.pre, (__half*)a.out, a.dm, ry, reverse);
+    else if (np == 8)
+        k_sharpen_fast_f32<2><<<grid, block, 0, s>>>((const float*)a.pre, (float*)a.out, a.dm, ry, reverse);
+    else
+        k_sharpen_fast_f32<1><<<grid, block, 0, s>>>((const float*)a.pre, (float*)a.out, a.dm, ry, reverse);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_sharpen_kernel(cudaStream_t s, const SharpenArgs& a) {
+    if (sharpen_fast_applies(a)) return launch_sharpen_fast(s, a);
     const int bx = sharpen_rows_block(a.dm.up_w);
     if (bx > 0) {   // vectorised rolling-window kernel
         constexpr int RY = kSharpenRowsPerThread;
