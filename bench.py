@@ -142,6 +142,8 @@ def run_reference(args):
     x = vo.synthetic_frame("noise", w, h)
     if prec == 2:
         x = x.astype(np.float16)
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1:
+        time.sleep(3.0)   # torchrun: let the idle ranks finish importing and exit before the host cores are timed
     for _ in range(min(args.warmup, 2)):
         vo.upscale_frame(x, up, s, prec, dtype=np.float32, workers=cores)
     t0 = time.perf_counter()
@@ -163,13 +165,29 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------ GPU arm
+def bind_to_gpu_numa_node(gpu_index):
+    """pin this rank to the CPUs NVML reports as local to its GPU before any pinned allocation (first-touch
+    puts the staging buffers on that node); returns a short description for the JSON line"""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        cpus = sorted(os.sched_getaffinity(0))
+        return f"{len(cpus)} cpus [{cpus[0]}..{cpus[-1]}] (nvmlDeviceSetCpuAffinity)"
+    except Exception as e:  # noqa: BLE001
+        return f"unchanged ({type(e).__name__})"
+
+
 def run_b200(args):
     import torch
     import vkresample_b200 as vb
+    from vkresample_b200 import sharding
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    affinity = bind_to_gpu_numa_node(local) if (world > 1 and not args.no_affinity) else "unchanged (single rank)"
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -183,8 +201,7 @@ def run_b200(args):
     dev = torch.device("cuda", local)
 
     w, h, up, prec, s = CONFIGS[args.config]
-    F = args.frames_per_step
-    plan_flags = vb.FLAG_FAST_SHARPEN if args.fast_sharpen else 0
+    plan_flags = vb.FLAG_EXACT_SHARPEN if args.exact_sharpen else 0
     plan = vb.Plan(w, h, up, prec, s, device=local, flags=plan_flags)
     plan.set_lanes(args.lanes)
     elem = 2 if prec == 2 else 4
@@ -209,16 +226,36 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step(i0):
-        for f in range(F):
+    def allmax(v):
+        t_ = torch.tensor([v], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(t_, op=dist.ReduceOp.MAX)
+        return float(t_.item())
+
+    def run_frames(p, n, i0=0):
+        for f in range(n):
             k = (i0 + f) % ring
-            plan.enqueue_device(d_in[k].data_ptr(), d_out[k].data_ptr())
+            p.enqueue_device(d_in[k].data_ptr(), d_out[k].data_ptr())
+
+    # ---- calibration (untimed): frames per step such that the timed region lasts >= --min-seconds
+    run_frames(plan, 4 * ring)
+    plan.synchronize()
+    plan.timer_start(); run_frames(plan, 8 * ring); t_cal = plan.timer_stop() * 1e-3 / (8 * ring)
+    t_cal = allmax(t_cal)
+    F = args.frames_per_step
+    if F <= 0:
+        F = int(np.ceil(args.min_seconds / (args.steps * t_cal)))
+        F = max(ring, -(-F // ring) * ring)
+    # the stream of one step, sharded like the reference's file loop (VkResample.cpp:1622-1629):
+    # global frame f (1-based) -> rank (f-1) mod world; every rank owns exactly F of the world*F frames
+    mine = sharding.frames_for_worker(world * F, world, rank)
+    assert len(mine) == F and all((f - 1) % world == rank for f in mine)
 
     sampler = ClockSampler(local)
     sampler.start()                  # runs through warm-up and the timed region; summarised per window below
     time.sleep(0.05)
     for i in range(args.warmup):
-        step(i * F)
+        run_frames(plan, F, i * F)
     plan.synchronize()
 
     launches0 = plan.launch_count
@@ -226,102 +263,114 @@ def run_b200(args):
     t_wall0 = time.perf_counter()
     plan.timer_start()
     for i in range(args.steps):
-        step(i * F)
+        run_frames(plan, F, i * F)
     ms = plan.timer_stop()          # CUDA events on the launching stream
     t_wall1 = time.perf_counter()
     t_wall = t_wall1 - t_wall0
     clocks = sampler.stop(t_wall0, t_wall1)
     barrier()
     launches = plan.launch_count - launches0
+    ms_max = allmax(ms)
+    value = sharding.aggregate_frames_per_s(args.steps * F, world, ms_max * 1e-3)
 
-    t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    value = world * args.steps * F / (ms_max * 1e-3)
+    # ---- burst figure (round 1's timed region: 20 x 32 frames, ~0.08 s) beside the sustained one
+    barrier()
+    plan.timer_start(); run_frames(plan, 640); ms_b = allmax(plan.timer_stop())
+    burst = {"value": world * 640 / (ms_b * 1e-3), "unit": UNIT, "frames": 640, "timed_region_s": ms_b * 1e-3}
 
-    # ---- the same device-resident measurement with B2R_FLAG_FAST_SHARPEN (approximate divisions / sqrt in the
-    # sharpen, within 2e-6 of the default); reported beside the headline, never instead of it
-    fast = None
-    if not args.fast_sharpen and not args.no_fast_leg:
-        with vb.Plan(w, h, up, prec, s, device=local, flags=vb.FLAG_FAST_SHARPEN) as pf:
-            pf.set_lanes(args.lanes)
-            f_steps = max(1, min(args.steps, 10))
-
-            def fstep(i0):
-                for f in range(F):
-                    k = (i0 + f) % ring
-                    pf.enqueue_device(d_in[k].data_ptr(), d_out[k].data_ptr())
-            for i in range(3):
-                fstep(i * F)
-            pf.synchronize()
+    # ---- the same device-resident measurement with B2R_FLAG_EXACT_SHARPEN (bit-exact sharpen kernels);
+    # reported beside the headline, never instead of it
+    exact = None
+    if not args.exact_sharpen and not args.no_exact_leg:
+        with vb.Plan(w, h, up, prec, s, device=local, flags=vb.FLAG_EXACT_SHARPEN) as px:
+            px.set_lanes(args.lanes)
+            n_x = max(ring, min(F * args.steps, 2048))
+            run_frames(px, 3 * ring)
+            px.synchronize()
             barrier()
-            pf.timer_start()
-            for i in range(f_steps):
-                fstep(i * F)
-            ms_f = pf.timer_stop()
+            px.timer_start(); run_frames(px, n_x); ms_x = allmax(px.timer_stop())
             barrier()
-            tf = torch.tensor([ms_f], dtype=torch.float64, device=dev)
-            if dist is not None:
-                dist.all_reduce(tf, op=dist.ReduceOp.MAX)
             t_dt = torch.float16 if prec == 2 else torch.float32
             scratch = torch.empty(plan.output_bytes, dtype=torch.uint8, device=dev)
-            pf.enqueue_device(d_in[0].data_ptr(), scratch.data_ptr()); pf.synchronize()
+            px.enqueue_device(d_in[0].data_ptr(), scratch.data_ptr()); px.synchronize()
             plan.enqueue_device(d_in[0].data_ptr(), d_out[0].data_ptr()); plan.synchronize()
             diff = float((scratch.view(t_dt).float() - d_out[0].view(t_dt).float()).abs().max().item())
-            pkf = pf.profile_kernels(10)
-            fast = {"value": world * f_steps * F / (float(tf.item()) * 1e-3), "unit": "frames/s", "steps": f_steps,
-                    "flag": "B2R_FLAG_FAST_SHARPEN", "sharpen_us": round(pkf["sharpen"] * 1e3, 2),
-                    "max_abs_vs_default_output": diff}
+            pkx = px.profile_kernels(10)
+            exact = {"value": world * n_x / (ms_x * 1e-3), "unit": UNIT, "frames": n_x,
+                     "flag": "B2R_FLAG_EXACT_SHARPEN", "sharpen_us": round(pkx["sharpen"] * 1e3, 2),
+                     "max_abs_default_vs_exact_output": diff}
             del scratch
 
     # ---- end to end through the C-ABI with pinned HOST buffers: per frame H2D + frame + D2H, frames
-    # rotating over the plan's lanes so that the copies of one frame overlap the kernels of another
-    e_frames = max(4, min(F, 16))
-    n_host = 2 * args.lanes   # multiple of the lane count (same reason as the device ring)
+    # rotating over the plan's lanes so that the copies of one frame overlap the kernels of another.
+    # No drain between steps: buffer k is always used by lane k mod lanes (n_host is a multiple of the lane
+    # count), so stream order alone keeps frames that share a buffer apart; one synchronize ends the region.
+    n_host = 2 * args.lanes
     h_in = [torch.from_numpy(plan.pack_input(rng.random((3, h, w), dtype=np.float32).astype(np_dt)).view(np.uint8)).pin_memory()
             for _ in range(n_host)]
     h_out = [torch.empty(plan.output_bytes, dtype=torch.uint8).pin_memory() for _ in range(n_host)]
-    for i in range(n_host):
-        plan.enqueue_host(h_in[i].data_ptr(), h_out[i].data_ptr())
-    plan.synchronize()
-    e_steps = max(1, min(args.steps, 5))
-    barrier()
-    t0 = time.perf_counter()
-    for st in range(e_steps):
-        for i in range(e_frames):
-            k = (st * e_frames + i) % n_host
-            plan.enqueue_host(h_in[k].data_ptr(), h_out[k].data_ptr())
-        plan.synchronize()          # every step's results are on the host before the next step starts
-    e_dt = time.perf_counter() - t0
-    te = torch.tensor([e_dt], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * e_steps * e_frames / float(te.item())
-    # ---- the same through the byte-pixel extension (u8 RGB in -> u8 RGB out, conversions on the GPU)
     u_in = [torch.from_numpy(rng.integers(0, 256, (h, w, 3), dtype=np.uint8)).pin_memory() for _ in range(n_host)]
     u_out = [torch.empty((plan.up_h, plan.up_w, 3), dtype=torch.uint8).pin_memory() for _ in range(n_host)]
-    for i in range(n_host):
-        plan.enqueue_host_u8(u_in[i].data_ptr(), u_out[i].data_ptr())
-    plan.synchronize()
-    barrier()
-    t0 = time.perf_counter()
-    for st in range(e_steps):
-        for i in range(e_frames):
-            k = (st * e_frames + i) % n_host
-            plan.enqueue_host_u8(u_in[k].data_ptr(), u_out[k].data_ptr())
+    e_steps = max(1, min(args.steps, 5))
+
+    def timed_host_leg(enq, bufs_in, bufs_out, min_s):
+        for i in range(n_host):
+            enq(bufs_in[i].data_ptr(), bufs_out[i].data_ptr())
         plan.synchronize()
-    u_dt = time.perf_counter() - t0
-    tu = torch.tensor([u_dt], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(tu, op=dist.ReduceOp.MAX)
-    e2e_u8_value = world * e_steps * e_frames / float(tu.item())
+        t0 = time.perf_counter()
+        for i in range(2 * n_host):
+            enq(bufs_in[i % n_host].data_ptr(), bufs_out[i % n_host].data_ptr())
+        plan.synchronize()
+        per = allmax((time.perf_counter() - t0) / (2 * n_host))   # calibration: slowest rank's seconds per frame
+        frames = max(n_host, int(np.ceil(min_s / (e_steps * per))))
+        frames = -(-frames // n_host) * n_host
+        barrier()
+        t0 = time.perf_counter()
+        for st in range(e_steps):
+            for i in range(frames):
+                k = (st * frames + i) % n_host
+                enq(bufs_in[k].data_ptr(), bufs_out[k].data_ptr())
+        plan.synchronize()
+        dt = allmax(time.perf_counter() - t0)
+        return world * e_steps * frames / dt, frames, dt
+
+    def copy_ceiling(bufs_in, bufs_out, nbytes_in, nbytes_out, frames):
+        """bare pinned H2D + D2H of the same bytes per frame on `lanes` streams, no kernels"""
+        streams = [torch.cuda.Stream(device=dev) for _ in range(args.lanes)]
+        dd_in = [torch.empty(nbytes_in, dtype=torch.uint8, device=dev) for _ in range(args.lanes)]
+        dd_out = [torch.empty(nbytes_out, dtype=torch.uint8, device=dev) for _ in range(args.lanes)]
+        flat_in = [b.view(-1) if b.dtype == torch.uint8 else b.view(torch.uint8).view(-1) for b in bufs_in]
+        flat_out = [b.view(-1) if b.dtype == torch.uint8 else b.view(torch.uint8).view(-1) for b in bufs_out]
+
+        def go(n):
+            for i in range(n):
+                k, l = i % n_host, i % args.lanes
+                with torch.cuda.stream(streams[l]):
+                    dd_in[l].copy_(flat_in[k], non_blocking=True)
+                    flat_out[k].copy_(dd_out[l], non_blocking=True)
+            for st_ in streams:
+                st_.synchronize()
+        go(n_host)
+        barrier()
+        t0 = time.perf_counter()
+        go(e_steps * frames)
+        dt = allmax(time.perf_counter() - t0)
+        return world * e_steps * frames / dt
+
+    e2e_value, e_frames, e_dt = timed_host_leg(plan.enqueue_host, h_in, h_out, args.min_seconds_e2e)
+    e2e_ceiling = copy_ceiling(h_in, h_out, plan.input_bytes, plan.output_bytes, e_frames)
+    # ---- the same through the byte-pixel extension (u8 RGB in -> u8 RGB out, conversions on the GPU)
+    e2e_u8_value, u_frames, u_dt = timed_host_leg(plan.enqueue_host_u8, u_in, u_out, args.min_seconds_e2e)
+    e2e_u8_ceiling = copy_ceiling(u_in, u_out, 3 * w * h, 3 * plan.up_w * plan.up_h, u_frames)
 
     result_checksum = float(np.frombuffer(h_out[0].numpy().tobytes()[:4096], dtype=np_dt).astype(np.float64).sum())
 
     # ---- roofline of the dominant kernel (separate pass, events between kernels, same workload)
     pk = plan.profile_kernels(20)
     alg = kernel_algorithmic_bytes(w, h, plan.up_w, plan.up_h, elem)
+    if pk.get("sharpen", 0.0) == 0.0 and "c2r_rows" in pk:   # fused C2R + sharpen: one kernel, no pre-sharpen plane
+        pk = {"r2c_rows": pk["r2c_rows"], "cols": pk["cols"], "c2r_sharpen": pk["c2r_rows"]}
+        alg["c2r_sharpen"] = alg["c2r_rows"]   # S2 in + output once (the pre-sharpen plane never reaches HBM)
     dom = max(pk, key=pk.get)
     peak, peak_src = peaks()
     achieved = alg[dom] / (pk[dom] * 1e-3) / 1e9
@@ -352,27 +401,38 @@ def run_b200(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32" if prec == 0 else "f16 storage / f32 FFT",
                 "data": "synthetic",
                 "config": {"workload": workload_name(args.config), "frames_per_step": F, "frames_per_gpu_per_step": F,
-                           "parallelism": f"frames sharded over {world} GPU(s), no collective",
+                           "timed_region_s": ms_max * 1e-3,
+                           "parallelism": f"frames sharded over {world} GPU(s) (frame f -> rank (f-1) mod {world}), no collective",
                            "l2": f"ring of {ring} distinct device-resident frames ({ring * (plan.input_bytes + plan.output_bytes) >> 20} MiB in+out, "
                                  f"~{(alg['r2c_rows'] + alg['cols'] + alg['c2r_rows'] + alg['sharpen']) >> 20} MiB touched per frame) > 126 MB L2",
                            "lanes": int(plan.lanes),
                            "radix_schedule": plan.radix_schedule(), "column_tile": int(plan.info.column_tile),
                            "static_kernels": int(plan.info.static_kernels),
-                           "sharpen_arithmetic": "approximate div/sqrt (B2R_FLAG_FAST_SHARPEN)" if args.fast_sharpen
-                                                 else "correctly rounded, bit-identical to the oracle (default)"},
+                           "kernels_per_frame": int(plan.info.kernels_per_frame),
+                           "cpu_affinity": affinity,
+                           "sharpen_arithmetic": "correctly rounded, bit-identical to the oracle (B2R_FLAG_EXACT_SHARPEN)" if args.exact_sharpen
+                                                 else "tolerance-bound (default): within 1e-5 fp32 / 1e-2 fp16 of oracle.sharpen on the same plane"},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": e_frames * plan.input_bytes,
                         "d2h_bytes_per_step": e_frames * plan.output_bytes, "frames_per_step": e_frames,
-                        "steps": e_steps, "api": "b2r_enqueue_host + b2r_synchronize (pinned host in -> pinned host out)",
+                        "steps": e_steps, "timed_region_s": e_dt,
+                        "api": "b2r_enqueue_host + b2r_synchronize (pinned host in -> pinned host out)",
+                        "copy_ceiling": e2e_ceiling, "frac_of_copy_ceiling": e2e_value / e2e_ceiling,
+                        "copy_ceiling_gb_s": e2e_ceiling * (plan.input_bytes + plan.output_bytes) / 1e9,
                         "checksum": result_checksum},
-                "e2e_u8": {"value": e2e_u8_value, "unit": UNIT, "h2d_bytes_per_step": e_frames * 3 * w * h,
-                           "d2h_bytes_per_step": e_frames * 3 * plan.up_w * plan.up_h, "frames_per_step": e_frames,
-                           "steps": e_steps, "api": "b2r_enqueue_host_u8 (u8 RGB in -> u8 RGB out, /255 fill and truncating "
-                                                    "quantiser of launchResample run on the GPU)",
+                "e2e_u8": {"value": e2e_u8_value, "unit": UNIT, "h2d_bytes_per_step": u_frames * 3 * w * h,
+                           "d2h_bytes_per_step": u_frames * 3 * plan.up_w * plan.up_h, "frames_per_step": u_frames,
+                           "steps": e_steps, "timed_region_s": u_dt,
+                           "api": "b2r_enqueue_host_u8 (u8 RGB in -> u8 RGB out, /255 fill and truncating "
+                                  "quantiser of launchResample run on the GPU)",
+                           "copy_ceiling": e2e_u8_ceiling, "frac_of_copy_ceiling": e2e_u8_value / e2e_u8_ceiling,
+                           "copy_ceiling_gb_s": e2e_u8_ceiling * 3 * (w * h + plan.up_w * plan.up_h) / 1e9,
                            "checksum": int(u_out[0].numpy()[:8, :8].astype(np.int64).sum())},
+                "copy_ceiling_note": "bare pinned cudaMemcpyAsync H2D + D2H of the same bytes per frame on the same number of "
+                                     "streams, no kernels (torch copy_ on torch streams), all ranks at once, max over ranks",
                 "gpu_launches": int(launches), "wall_s_timed_region": t_wall,
-                "roofline": roofline, "clocks": clocks}
-        if fast:
-            line["fast_sharpen"] = fast
+                "burst": burst, "roofline": roofline, "clocks": clocks}
+        if exact:
+            line["exact_sharpen"] = exact
         if cpu:
             line["cpu_baseline"] = cpu
         emit(line)
@@ -389,16 +449,22 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
-    ap.add_argument("--frames-per-step", type=int, default=32)
+    ap.add_argument("--frames-per-step", type=int, default=0,
+                    help="frames per step per GPU; 0 (default): calibrated so that the timed region lasts >= --min-seconds")
+    ap.add_argument("--min-seconds", type=float, default=2.5, help="length of the device-resident timed region")
+    ap.add_argument("--min-seconds-e2e", type=float, default=1.2, help="length of each host-fed timed region")
+    ap.add_argument("--no-affinity", action="store_true", help="N > 1: do not bind ranks to their GPU's NUMA-local CPUs")
     ap.add_argument("--ring", type=int, default=8)
     ap.add_argument("--lanes", type=int, default=3,
                     help="concurrent frames in flight per GPU (like the reference's -numthreads on one device)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-fast-leg", action="store_true", help="skip the extra B2R_FLAG_FAST_SHARPEN measurement (profiling runs)")
-    ap.add_argument("--fast-sharpen", action="store_true",
-                    help="create the plan with B2R_FLAG_FAST_SHARPEN (not the default; recorded in config)")
+    ap.add_argument("--no-exact-leg", action="store_true", help="skip the extra B2R_FLAG_EXACT_SHARPEN measurement (profiling runs)")
+    ap.add_argument("--no-fast-leg", action="store_true", help="(round-1 name) same as --no-exact-leg")
+    ap.add_argument("--exact-sharpen", action="store_true",
+                    help="create the plan with B2R_FLAG_EXACT_SHARPEN (bit-exact sharpen; not the default; recorded in config)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    args.no_exact_leg = args.no_exact_leg or args.no_fast_leg
     # stdout carries exactly ONE JSON line: everything libraries print to fd 1 while we run (e.g. NCCL's
     # "NCCL version ..." banner under torchrun) is sent to stderr, the result line goes to the real stdout
     global _RESULT_FD

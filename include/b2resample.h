@@ -157,6 +157,18 @@ size_t b2r_plan_output_u8_bytes(const b2r_plan* plan);
 int b2r_upload_u8(b2r_plan* plan, const unsigned char* host_rgb);
 int b2r_download_u8(b2r_plan* plan, unsigned char* host_rgb);
 int b2r_enqueue_host_u8(b2r_plan* plan, const unsigned char* host_rgb_in, unsigned char* host_rgb_out);
+/* Completion tickets for the asynchronous host forms (pipelined batch front-ends: decode / encode threads
+ * around one submitting thread).  Every b2r_enqueue_host / b2r_enqueue_host_u8 call takes the next ticket
+ * (1, 2, 3, ...); b2r_plan_last_ticket returns the ticket of the most recent call; b2r_wait_ticket blocks until
+ * that frame's output is complete in host_out.  b2r_wait_ticket only waits on a CUDA event: it may be called
+ * from a different thread than the one that enqueues (the one exception to "one thread per plan").  The lane
+ * count must not change between an enqueue and its wait. */
+uint64_t b2r_plan_last_ticket(const b2r_plan* plan);
+int b2r_wait_ticket(b2r_plan* plan, uint64_t ticket);
+/* Pinned (page-locked) host memory for the asynchronous forms -- what the staging buffer of
+ * transferDataFromCPU / transferDataToCPU is to the reference (VkResample.cpp:385-473).  NULL on failure. */
+void* b2r_host_alloc(size_t bytes);
+void b2r_host_free(void* ptr);
 /* Number of lanes (1..8, default 1) that b2r_enqueue_device / b2r_enqueue_host rotate over.  Each
  * lane owns a stream and a private set of working buffers, so consecutive frames of a stream overlap
  * on the GPU (and copies overlap kernels) -- the equivalent of running the reference with

@@ -39,6 +39,7 @@ EXPORTS = [
     "b2r_plan_launch_count", "b2r_last_error", "b2r_version", "b2r_enqueue_device", "b2r_timer_start",
     "b2r_timer_stop", "b2r_profile_kernels", "b2r_enqueue_host", "b2r_plan_set_lanes", "b2r_plan_lanes",
     "b2r_plan_input_u8_bytes", "b2r_plan_output_u8_bytes", "b2r_upload_u8", "b2r_download_u8", "b2r_enqueue_host_u8",
+    "b2r_plan_last_ticket", "b2r_wait_ticket", "b2r_host_alloc", "b2r_host_free",
 ]
 
 
@@ -104,6 +105,13 @@ def load_library():
     L.b2r_upload_u8.argtypes = [vp, vp]
     L.b2r_download_u8.argtypes = [vp, vp]
     L.b2r_enqueue_host_u8.argtypes = [vp, vp, vp]
+    L.b2r_plan_last_ticket.argtypes = [vp]
+    L.b2r_plan_last_ticket.restype = ctypes.c_uint64
+    L.b2r_wait_ticket.argtypes = [vp, ctypes.c_uint64]
+    L.b2r_host_alloc.argtypes = [ctypes.c_size_t]
+    L.b2r_host_alloc.restype = vp
+    L.b2r_host_free.argtypes = [vp]
+    L.b2r_host_free.restype = None
     L.b2r_plan_set_lanes.argtypes = [vp, u32]
     L.b2r_plan_lanes.argtypes = [vp]
     L.b2r_plan_lanes.restype = u32
@@ -264,6 +272,14 @@ class Plan:
 
     def enqueue_host_u8(self, host_in, host_out):
         _check(self._lib.b2r_enqueue_host_u8(self._h, _ptr(host_in), _ptr(host_out)))
+
+    @property
+    def last_ticket(self) -> int:
+        return int(self._lib.b2r_plan_last_ticket(self._h))
+
+    def wait_ticket(self, ticket: int):
+        """block until the frame that took `ticket` (enqueue_host / enqueue_host_u8) has landed in its host buffer"""
+        _check(self._lib.b2r_wait_ticket(self._h, ticket))
 
     def set_lanes(self, lanes: int):
         _check(self._lib.b2r_plan_set_lanes(self._h, lanes))

@@ -17,6 +17,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <new>
 #include <string>
 #include <vector>
@@ -77,6 +78,8 @@ struct Lane {
     unsigned char* u8_out = nullptr;
 };
 
+constexpr int kTicketDepth = 4;        // completion events kept per lane (b2r_wait_ticket)
+
 struct b2r_plan {
     int device = 0;
     uint32_t flags = 0;
@@ -108,6 +111,15 @@ struct b2r_plan {
     std::string jit_note;       // why JIT was not used (if it was not)
     std::vector<Lane> extra;   // lanes 1..n-1
     uint32_t next_lane = 0;
+    // completion tickets (b2r_wait_ticket): per lane a ring of kTicketDepth events; tick_log remembers which
+    // event the last kTicketLog tickets were stamped with.  An event that was re-recorded since belongs to a
+    // LATER frame of the same in-order stream, so waiting on it still implies the older frame has finished.
+    std::vector<std::vector<cudaEvent_t>> tick_ev;
+    std::vector<uint32_t> tick_pos;
+    struct TickEntry { uint64_t ticket = 0; cudaEvent_t ev = nullptr; };
+    TickEntry tick_log[64];
+    std::mutex tick_mu;        // b2r_wait_ticket may run on another thread than the enqueuing one
+    uint64_t tickets = 0;
     Lane lane(uint32_t i) const {
         if (i == 0) { Lane l; l.stream = stream; l.d_in = d_in; l.d_pre = d_pre; l.d_out = d_out; l.d_spec1 = d_spec1; l.d_spec2 = d_spec2; l.done = ev1; l.d_nyq = d_nyq; return l; }
         return extra[i - 1];
@@ -449,6 +461,8 @@ void b2r_plan_destroy(b2r_plan* p) {
         cudaFree(l.u8_in); cudaFree(l.u8_out); cudaFree(l.d_nyq);
     }
     cudaFree(p->u8_in0); cudaFree(p->u8_out0);
+    for (auto& ring : p->tick_ev) for (auto e : ring) if (e) cudaEventDestroy(e);
+    p->tick_ev.clear();
     p->extra.clear();
     if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
     if (p->graph) cudaGraphDestroy(p->graph);
@@ -604,6 +618,25 @@ int b2r_plan_set_lanes(b2r_plan* p, uint32_t lanes) {
 
 uint32_t b2r_plan_lanes(const b2r_plan* p) { return p ? p->num_lanes() : 0; }
 
+namespace {
+// records the completion event of the frame just enqueued on lane li and advances the ticket counter
+int stamp_ticket(b2r_plan* p, uint32_t li, cudaStream_t s) {
+    const uint32_t nl = p->num_lanes();
+    std::lock_guard<std::mutex> g(p->tick_mu);
+    if (p->tick_ev.size() < nl) { p->tick_ev.resize(nl); p->tick_pos.resize(nl, 0); }
+    auto& ring = p->tick_ev[li];
+    if (ring.empty()) {
+        ring.resize(kTicketDepth, nullptr);
+        for (auto& e : ring) CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
+    cudaEvent_t ev = ring[p->tick_pos[li]++ % kTicketDepth];
+    CU(cudaEventRecord(ev, s));
+    const uint64_t t = ++p->tickets;
+    p->tick_log[t % 64] = b2r_plan::TickEntry{t, ev};
+    return B2R_SUCCESS;
+}
+}  // namespace
+
 int b2r_enqueue_device(b2r_plan* p, const void* d_in, void* d_out) {
     if (!p || !d_in || !d_out) return fail(B2R_ERR_INVALID_ARG, "null argument");
     CU(cudaSetDevice(p->device));
@@ -625,7 +658,7 @@ int b2r_enqueue_host(b2r_plan* p, const void* host_in, void* host_out) {
     if (rc) return rc;
     p->launches += p->kernels_per_frame;
     CU(cudaMemcpyAsync(host_out, l.d_out, p->g.output_bytes(), cudaMemcpyDeviceToHost, l.stream));
-    return B2R_SUCCESS;
+    return stamp_ticket(p, li, l.stream);
 }
 
 size_t b2r_plan_input_u8_bytes(const b2r_plan* p) { return p ? 3ull * p->g.w * p->g.h : 0; }
@@ -690,8 +723,32 @@ int b2r_enqueue_host_u8(b2r_plan* p, const unsigned char* host_in, unsigned char
     else CU(launch_planar_to_u8(l.stream, l.d_out, out, p->dm, p->g.precision));
     p->launches += p->kernels_per_frame + 2;
     CU(cudaMemcpyAsync(host_out, out, b2r_plan_output_u8_bytes(p), cudaMemcpyDeviceToHost, l.stream));
-    return B2R_SUCCESS;
+    return stamp_ticket(p, li, l.stream);
 }
+
+uint64_t b2r_plan_last_ticket(const b2r_plan* p) { return p ? p->tickets : 0; }
+
+int b2r_wait_ticket(b2r_plan* p, uint64_t ticket) {
+    if (!p || ticket == 0) return fail(B2R_ERR_INVALID_ARG, "no such ticket");
+    cudaEvent_t ev = nullptr;
+    {
+        std::lock_guard<std::mutex> g(p->tick_mu);
+        if (ticket > p->tickets) return fail(B2R_ERR_INVALID_ARG, "no such ticket");
+        if (p->tick_log[ticket % 64].ticket == ticket) ev = p->tick_log[ticket % 64].ev;
+    }
+    if (ev) { CU(cudaEventSynchronize(ev)); return B2R_SUCCESS; }
+    return b2r_synchronize(p);   // older than the log: everything enqueued so far covers it
+}
+
+void* b2r_host_alloc(size_t bytes) {
+    void* ptr = nullptr;
+    if (cudaHostAlloc(&ptr, bytes, cudaHostAllocDefault) != cudaSuccess) {
+        fail(B2R_ERR_NOMEM, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+        return nullptr;
+    }
+    return ptr;
+}
+void b2r_host_free(void* ptr) { if (ptr) cudaFreeHost(ptr); }
 
 int b2r_timer_start(b2r_plan* p) {
     if (!p) return fail(B2R_ERR_INVALID_ARG, "null plan");

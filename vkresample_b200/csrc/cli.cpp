@@ -9,9 +9,22 @@
 // zlib-based codec (the reference vendors stb_image; the image has zlib only).
 // Additions: -gpus N spreads the worker threads over N CUDA devices (thread t -> device
 // (d + t) % N); everything else behaves like the reference.
+//
+// Batch mode (-ifolder) has two engines:
+//   * -sync: the reference's loop, one frame at a time per worker thread (decode -> upload -> execute ->
+//     download -> encode), the worker threads sharing nothing but the GPU (VkResample.cpp:1627-1754);
+//   * default: a PIPELINE per GPU -- -numthreads codec workers decode PNGs straight into a ring of pinned
+//     host slots and encode finished slots, one submitting thread feeds b2r_enqueue_host_u8 over several
+//     lanes (H2D copy, u8->planar, the 4 frame kernels, planar->u8, D2H copy of different frames overlap),
+//     completion through b2r_wait_ticket.  Same files, same bytes as -sync (tests/test_cli.py), in the
+//     reference's frame -> worker striding across GPUs (frame f, 1-based, -> GPU (f-1) mod gpus).
 #include <zlib.h>
 
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <mutex>
+#include <new>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -37,7 +50,10 @@ static int paeth(int a, int b, int c) {
 
 // Decodes a non-interlaced PNG to 8-bit RGB (what stbi_load(..., 3) hands the reference:
 // grey is replicated, alpha is dropped, 16-bit samples keep their high byte).
-static bool load_rgb(const char* path, std::vector<unsigned char>* rgb, int* w, int* h, std::string* err) {
+// `dst` (optional): caller-provided buffer of dst_cap bytes that receives the pixels instead of *rgb (the
+// pipelined batch mode decodes straight into pinned memory); the image must then be exactly want_w x want_h.
+static bool load_rgb_impl(const char* path, std::vector<unsigned char>* rgb, int* w, int* h, std::string* err,
+                          unsigned char* dst, size_t dst_cap) {
     FILE* f = fopen(path, "rb");
     if (!f) { *err = "cannot open file"; return false; }
     std::vector<unsigned char> buf;
@@ -56,8 +72,12 @@ static bool load_rgb(const char* path, std::vector<unsigned char>* rgb, int* w, 
         const unsigned char* data = &buf[pos + 8];
         if (pos + 12 + len > buf.size()) { *err = "truncated PNG"; return false; }
         if (!memcmp(type, "IHDR", 4)) {
-            width = (int)be32(data); height = (int)be32(data + 4);
+            if (len != 13) { *err = "bad IHDR chunk length"; return false; }
+            const uint32_t uw = be32(data), uh = be32(data + 4);
+            if (uw == 0 || uh == 0 || uw >= 65536u || uh >= 65536u) { *err = "image dimensions out of range (1..65535)"; return false; }
+            width = (int)uw; height = (int)uh;
             depth = data[8]; ctype = data[9]; interlace = data[12];
+            if (data[10] != 0 || data[11] != 0) { *err = "unknown PNG compression / filter method"; return false; }
         } else if (!memcmp(type, "PLTE", 4)) {
             plte.assign(data, data + len);
         } else if (!memcmp(type, "IDAT", 4)) {
@@ -68,7 +88,9 @@ static bool load_rgb(const char* path, std::vector<unsigned char>* rgb, int* w, 
         pos += 12 + len;
     }
     if (width <= 0 || height <= 0) { *err = "missing IHDR"; return false; }
-    if (interlace) { *err = "interlaced PNG is not supported"; return false; }
+    if (interlace) { *err = "interlaced (Adam7) PNG is not supported"; return false; }
+    if (ctype == 3 && plte.empty()) { *err = "palette image without PLTE chunk"; return false; }
+    if (idat.empty()) { *err = "no IDAT chunk"; return false; }
     int channels = (ctype == 0) ? 1 : (ctype == 2) ? 3 : (ctype == 3) ? 1 : (ctype == 4) ? 2 : (ctype == 6) ? 4 : 0;
     if (!channels || (depth != 8 && depth != 16 && !(depth < 8 && (ctype == 0 || ctype == 3)))) {
         *err = "unsupported PNG colour type / bit depth"; return false;
@@ -82,7 +104,13 @@ static bool load_rgb(const char* path, std::vector<unsigned char>* rgb, int* w, 
         *err = "zlib inflate failed"; return false;
     }
     std::vector<unsigned char> prev(stride, 0), cur(stride);
-    rgb->assign((size_t)width * height * 3, 0);
+    unsigned char* pix = dst;
+    if (pix) {
+        if ((size_t)width * height * 3 != dst_cap) { *err = "image has a different size than the first one"; return false; }
+    } else {
+        rgb->assign((size_t)width * height * 3, 0);
+        pix = rgb->data();
+    }
     for (int y = 0; y < height; ++y) {
         const unsigned char* row = &raw[(stride + 1) * y];
         const int ft = row[0];
@@ -98,7 +126,7 @@ static bool load_rgb(const char* path, std::vector<unsigned char>* rgb, int* w, 
             }
             cur[i] = (unsigned char)x;
         }
-        unsigned char* out = &(*rgb)[(size_t)y * width * 3];
+        unsigned char* out = pix + (size_t)y * width * 3;
         for (int x = 0; x < width; ++x) {
             unsigned char s[4] = {0, 0, 0, 255};
             if (depth == 8) for (int c = 0; c < channels; ++c) s[c] = cur[(size_t)x * channels + c];
@@ -121,8 +149,18 @@ static bool load_rgb(const char* path, std::vector<unsigned char>* rgb, int* w, 
     *w = width; *h = height;
     return true;
 }
+static bool load_rgb(const char* path, std::vector<unsigned char>* rgb, int* w, int* h, std::string* err,
+                     unsigned char* dst = nullptr, size_t dst_cap = 0) {
+    try {
+        return load_rgb_impl(path, rgb, w, h, err, dst, dst_cap);
+    } catch (const std::bad_alloc&) {
+        *err = "out of memory while decoding";
+        return false;
+    }
+}
 
 // 8-bit RGB encoder with per-row adaptive filtering (minimum sum of absolute differences)
+static int g_zlevel = 6;   // -pnglevel
 static bool write_rgb(const char* path, const unsigned char* rgb, int w, int h) {
     const size_t stride = (size_t)w * 3;
     std::vector<unsigned char> raw((stride + 1) * h), cand(stride), best(stride);
@@ -146,7 +184,7 @@ static bool write_rgb(const char* path, const unsigned char* rgb, int w, int h) 
     }
     uLongf zlen = compressBound(raw.size());
     std::vector<unsigned char> z(zlen);
-    if (compress2(z.data(), &zlen, raw.data(), raw.size(), 6) != Z_OK) return false;
+    if (compress2(z.data(), &zlen, raw.data(), raw.size(), g_zlevel) != Z_OK) return false;
     std::vector<unsigned char> out = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
     auto chunk = [&](const char* type, const unsigned char* data, size_t len) {
         put32(out, (uint32_t)len);
@@ -174,7 +212,7 @@ static bool write_rgb(const char* path, const unsigned char* rgb, int w, int h) 
 // ------------------------------------------------------------------------------------------- CLI
 struct Config {  // VkResampleConfiguration, VkResample.cpp:45-59
     uint32_t device_id = 0, upload_files = 0, num_iter = 1, precision = 0, num_threads = 1, thread_id = 0;
-    uint32_t num_files = 1, gpus = 1, c2c = 0, fast = 0;
+    uint32_t num_files = 1, gpus = 1, c2c = 0, fast = 0, exact = 0, sync = 0, lanes = 3;
     float upscale = 1.0f, sharpen = 0.2f;
     const char* input = nullptr;
     const char* output = nullptr;
@@ -191,7 +229,24 @@ static char* flag_value(char** start, char** end, const std::string& flag) {    
     return nullptr;
 }
 
-// launchResample, VkResample.cpp:1280-1780
+static uint32_t plan_flags(const Config& cfg) {
+    return (cfg.c2c ? B2R_FLAG_C2C_PARITY : B2R_FLAG_NONE) | (cfg.fast ? B2R_FLAG_FAST_SHARPEN : B2R_FLAG_NONE) |
+           (cfg.exact ? B2R_FLAG_EXACT_SHARPEN : B2R_FLAG_NONE);
+}
+
+// one-line notices about behaviour a VkResample user would not expect silently (printed once per process)
+static void plan_notices(const Config& cfg, const b2r_plan_info& info) {
+    static std::atomic<bool> said{false};
+    if (said.exchange(true)) return;
+    if (!cfg.c2c && info.up_w > 6144)
+        printf("Note: VkResample itself switches to its C2C branch for upscaled widths > 6144 on NVIDIA Vulkan "
+               "(VkResample.cpp:1424); this run keeps R2C/C2R semantics -- pass -c2c to reproduce that branch.\n");
+    if (info.static_kernels != 7u)
+        printf("Warning: no statically scheduled kernels for this size (%s); running the any-size kernels at about half speed.\n",
+               info.jit_note[0] ? info.jit_note : "plan-time JIT disabled");
+}
+
+// launchResample, VkResample.cpp:1280-1780 (the reference's synchronous per-thread frame loop; batch mode: -sync)
 static int launch_resample(Config cfg) {
     const int ndev = b2r_device_count();
     if (ndev < 1) { printf("No CUDA device found: %s\n", b2r_last_error()); return -1; }
@@ -203,14 +258,14 @@ static int launch_resample(Config cfg) {
     std::vector<unsigned char> rgb;
     int w = 0, h = 0;
     std::string err;
-    if (!png::load_rgb(name, &rgb, &w, &h, &err)) { printf("Image not found\n"); return 5; /* VK_INCOMPLETE */ }
+    if (!png::load_rgb(name, &rgb, &w, &h, &err)) { printf("Image not found (%s: %s)\n", name, err.c_str()); return 5; /* VK_INCOMPLETE */ }
 
     b2r_plan* plan = nullptr;
-    int rc = b2r_plan_create(&plan, device, (uint32_t)w, (uint32_t)h, cfg.upscale, cfg.precision, cfg.sharpen,
-                             (cfg.c2c ? B2R_FLAG_C2C_PARITY : B2R_FLAG_NONE) | (cfg.fast ? B2R_FLAG_FAST_SHARPEN : B2R_FLAG_NONE));
+    int rc = b2r_plan_create(&plan, device, (uint32_t)w, (uint32_t)h, cfg.upscale, cfg.precision, cfg.sharpen, plan_flags(cfg));
     if (rc) { printf("Plan creation failed, error code: %d (%s)\n", rc, b2r_last_error()); return rc; }
     b2r_plan_info info;
     b2r_plan_get_info(plan, &info);
+    plan_notices(cfg, info);
     if (cfg.thread_id == 0)
         printf("VRAM per thread: %d MB Total: %d MB\n", (int)(info.device_bytes >> 20), (int)(cfg.num_threads * (info.device_bytes >> 20)));
     const size_t out_plane = (size_t)info.up_w * info.up_h;
@@ -225,7 +280,7 @@ static int launch_resample(Config cfg) {
         if (f > 0) {
             snprintf(name, sizeof name, "%s/%06d.png", cfg.ifolder, f * cfg.num_threads + cfg.thread_id + 1);
             int w2, h2;
-            if (!png::load_rgb(name, &rgb, &w2, &h2, &err)) { printf("Image not found\n"); return 5; }
+            if (!png::load_rgb(name, &rgb, &w2, &h2, &err)) { printf("Image not found (%s: %s)\n", name, err.c_str()); return 5; }
             if (w2 != w || h2 != h) { printf("Image %s has a different size\n", name); return -1; }
         }
         // u8 HWC -> planar [0,1] (VkResample.cpp:1636-1685) runs on the GPU: b2r_upload_u8 ships the
@@ -250,6 +305,139 @@ static int launch_resample(Config cfg) {
     return 0;
 }
 
+// ------------------------------------------------------------------------------- pipelined batch mode
+// One Pipeline per GPU.  Frame k of this GPU (global file number first + k*stride, 1-based) lives in ring slot
+// k % R from "decode claimed" to "encoded and written":
+//     FREE -> DECODING -> DECODED -> SUBMITTED -> (encode claimed) -> FREE
+// Codec workers take the oldest unclaimed encode job if there is one (it frees a slot), else the next decode
+// job whose slot is free; the submitting thread hands DECODED slots to b2r_enqueue_host_u8 in frame order and
+// records the ticket; an encoder waits for its ticket (b2r_wait_ticket, thread-safe) before reading the slot.
+struct Pipeline {
+    Config cfg;
+    int gpu_index = 0, device = 0, w = 0, h = 0;
+    uint32_t first = 1, stride = 1, total = 0;       // this GPU's files: first, first+stride, ...
+    b2r_plan* plan = nullptr;
+    b2r_plan_info info{};
+    enum State { FREE, DECODING, DECODED, SUBMITTED };
+    struct Slot { unsigned char* in = nullptr; unsigned char* out = nullptr; State state = FREE; uint64_t ticket = 0; };
+    std::vector<Slot> slots;
+    std::mutex mu;
+    std::condition_variable cv;
+    uint32_t next_decode = 0, next_submit = 0, next_encode = 0, written = 0;
+    int error = 0;
+    double t_decode = 0, t_encode = 0, t_wait = 0;    // summed over workers (seconds)
+
+    uint32_t file_of(uint32_t k) const { return first + k * stride; }
+
+    void fail_with(int rc) { std::lock_guard<std::mutex> g(mu); if (!error) error = rc ? rc : -1; cv.notify_all(); }
+
+    void submit_loop() {
+        for (uint32_t k = 0; k < total; ++k) {
+            Slot& s = slots[k % slots.size()];
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return error || s.state == DECODED; });
+                if (error) return;
+            }
+            int rc = b2r_enqueue_host_u8(plan, s.in, s.out);
+            if (rc) { printf("enqueue failed: %s\n", b2r_last_error()); fail_with(rc); return; }
+            std::lock_guard<std::mutex> g(mu);
+            s.ticket = b2r_plan_last_ticket(plan);
+            s.state = SUBMITTED;
+            next_submit = k + 1;
+            cv.notify_all();
+        }
+    }
+
+    void worker_loop() {
+        using clk = std::chrono::steady_clock;
+        char name[512];
+        std::string err;
+        for (;;) {
+            uint32_t k = 0; bool encode = false;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] {
+                    if (error || written == total) return true;
+                    if (next_encode < next_submit) return true;
+                    return next_decode < total && slots[next_decode % slots.size()].state == FREE;
+                });
+                if (error || written == total) return;
+                if (next_encode < next_submit) { k = next_encode++; encode = true; }
+                else { k = next_decode++; slots[k % slots.size()].state = DECODING; }
+            }
+            Slot& s = slots[k % slots.size()];
+            if (encode) {
+                auto t0 = clk::now();
+                int rc = b2r_wait_ticket(plan, s.ticket);
+                auto t1 = clk::now();
+                if (rc) { printf("wait failed: %s\n", b2r_last_error()); fail_with(rc); return; }
+                snprintf(name, sizeof name, "%s/%06u.png", cfg.ofolder, file_of(k));
+                if (!png::write_rgb(name, s.out, (int)info.up_w, (int)info.up_h)) printf("cannot write %s\n", name);
+                auto t2 = clk::now();
+                std::lock_guard<std::mutex> g(mu);
+                t_wait += std::chrono::duration<double>(t1 - t0).count();
+                t_encode += std::chrono::duration<double>(t2 - t1).count();
+                s.state = FREE;
+                ++written;
+                cv.notify_all();
+            } else {
+                auto t0 = clk::now();
+                snprintf(name, sizeof name, "%s/%06u.png", cfg.ifolder, file_of(k));
+                int w2 = 0, h2 = 0;
+                if (!png::load_rgb(name, nullptr, &w2, &h2, &err, s.in, (size_t)w * h * 3)) {
+                    printf("Image not found (%s: %s)\n", name, err.c_str());
+                    fail_with(5);
+                    return;
+                }
+                std::lock_guard<std::mutex> g(mu);
+                t_decode += std::chrono::duration<double>(clk::now() - t0).count();
+                s.state = DECODED;
+                cv.notify_all();
+            }
+        }
+    }
+
+    int run() {
+        const int ndev = b2r_device_count();
+        if (ndev < 1) { printf("No CUDA device found: %s\n", b2r_last_error()); return -1; }
+        device = (int)((cfg.device_id + (uint32_t)gpu_index) % (uint32_t)ndev);
+        char name[512];
+        snprintf(name, sizeof name, "%s/%06u.png", cfg.ifolder, file_of(0));
+        std::vector<unsigned char> probe;
+        std::string err;
+        if (!png::load_rgb(name, &probe, &w, &h, &err)) { printf("Image not found (%s: %s)\n", name, err.c_str()); return 5; }
+        int rc = b2r_plan_create(&plan, device, (uint32_t)w, (uint32_t)h, cfg.upscale, cfg.precision, cfg.sharpen, plan_flags(cfg));
+        if (rc) { printf("Plan creation failed, error code: %d (%s)\n", rc, b2r_last_error()); return rc; }
+        b2r_plan_get_info(plan, &info);
+        plan_notices(cfg, info);
+        const uint32_t lanes = std::max(1u, std::min(cfg.lanes, 8u));
+        if ((rc = b2r_plan_set_lanes(plan, lanes))) { printf("set_lanes failed: %s\n", b2r_last_error()); return rc; }
+        b2r_plan_get_info(plan, &info);
+        if (gpu_index == 0)
+            printf("VRAM per GPU: %d MB (%u lanes), %u codec threads + 1 submit thread per GPU\n", (int)(info.device_bytes >> 20), lanes, cfg.num_threads);
+        const size_t n_slots = std::min<size_t>(total, (size_t)cfg.num_threads + 2 * lanes + 2);
+        slots.resize(n_slots);
+        for (auto& s : slots) {
+            s.in = (unsigned char*)b2r_host_alloc(b2r_plan_input_u8_bytes(plan));
+            s.out = (unsigned char*)b2r_host_alloc(b2r_plan_output_u8_bytes(plan));
+            if (!s.in || !s.out) { printf("pinned allocation failed: %s\n", b2r_last_error()); return -4; }
+        }
+        std::vector<std::thread> th;
+        th.emplace_back([this] { submit_loop(); });
+        for (uint32_t t = 0; t < cfg.num_threads; ++t) th.emplace_back([this] { worker_loop(); });
+        for (auto& t : th) t.join();
+        b2r_synchronize(plan);
+        for (auto& s : slots) { b2r_host_free(s.in); b2r_host_free(s.out); }
+        char dev_name[256] = "";
+        b2r_device_name(device, dev_name, sizeof dev_name);
+        printf("GPU %d finished: %u frames, codec thread-seconds: decode %.2f, encode %.2f, waiting for the GPU %.2f. Device name: %s API:%s\n",
+               gpu_index, written, t_decode, t_encode, t_wait, dev_name, b2r_version());
+        b2r_plan_destroy(plan);
+        return error;
+    }
+};
+
 int main(int argc, char* argv[]) {
     Config cfg;
     cfg.upscale = 1.0f;   // reference defaults, VkResample.cpp:1798-1804
@@ -271,7 +459,12 @@ int main(int argc, char* argv[]) {
                "\t-gpus X: (extension) spread the worker threads over X CUDA devices (default 1)\n"
                "\t-c2c: (extension) reproduce the reference's C2C branch (what VkResample runs when the upscaled width\n"
                "\t      exceeds its shared-memory limit, e.g. > 6144 on NVIDIA); default is R2C/C2R at every size\n"
-               "\t-fast: (extension) approximate divisions / square root in the sharpen (B2R_FLAG_FAST_SHARPEN)\n");
+               "\t-exact: (extension) bit-exact sharpen arithmetic (B2R_FLAG_EXACT_SHARPEN; default: tolerance-bound kernels)\n"
+               "\t-fast: (round-1 extension, now the default behaviour; kept for compatibility)\n"
+               "\t-sync: (extension) batch mode as the reference runs it: every worker thread decodes, uploads, executes,\n"
+               "\t       downloads and encodes one frame at a time.  Default batch mode is a pipeline per GPU: -numthreads\n"
+               "\t       codec threads around a pinned ring, frames in flight on -lanes X streams (default 3)\n"
+               "\t-pnglevel X: (extension) zlib level of the PNG encoder, 0..9 (default 6)\n");
         return 0;
     }
     if (find_flag(argv, argv + argc, "-pngcopy")) {  // diagnostic: decode + re-encode (codec self-test, no GPU)
@@ -301,6 +494,10 @@ int main(int argc, char* argv[]) {
         return 1;
     cfg.c2c = find_flag(argv, argv + argc, "-c2c") ? 1u : 0u;
     cfg.fast = find_flag(argv, argv + argc, "-fast") ? 1u : 0u;
+    cfg.exact = find_flag(argv, argv + argc, "-exact") ? 1u : 0u;
+    cfg.sync = find_flag(argv, argv + argc, "-sync") ? 1u : 0u;
+    if (need("-lanes", "%u", &cfg.lanes) || need("-pnglevel", "%d", &png::g_zlevel)) return 1;
+    if (png::g_zlevel < 0 || png::g_zlevel > 9) png::g_zlevel = 6;
     if (find_flag(argv, argv + argc, "-ifolder")) {  // batch mode, VkResample.cpp:1893-1957
         cfg.upload_files = 1;
         cfg.ifolder = flag_value(argv, argv + argc, "-ifolder");
@@ -318,6 +515,27 @@ int main(int argc, char* argv[]) {
     if (cfg.num_threads < 1) cfg.num_threads = 1;
     if (cfg.gpus < 1) cfg.gpus = 1;
     auto t0 = std::chrono::steady_clock::now();
+    if (cfg.upload_files && !cfg.sync) {   // pipelined batch mode: one Pipeline per GPU, frame f -> GPU (f-1) mod gpus
+        printf("VkResample - FFT based upscaling\n");
+        const uint32_t g_used = std::min(cfg.gpus, std::max(1u, cfg.num_files));
+        std::vector<Pipeline> pipes(g_used);
+        std::vector<std::thread> th;
+        std::vector<int> prc(g_used, 0);
+        for (uint32_t g = 0; g < g_used; ++g) {
+            Pipeline& p = pipes[g];
+            p.cfg = cfg; p.gpu_index = (int)g; p.first = g + 1; p.stride = g_used;
+            p.total = (cfg.num_files > g) ? (cfg.num_files - g - 1) / g_used + 1 : 0;   // VkResample.cpp:1622-1626 with numThreads = gpus
+            th.emplace_back([&p, &prc, g] { prc[g] = p.total ? p.run() : 0; });
+        }
+        for (auto& t : th) t.join();
+        const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        uint32_t frames = 0;
+        for (auto& p : pipes) frames += p.written;
+        printf("Total time: %0.3f s\n", secs);
+        printf("Pipelined batch: %u frames on %u GPU(s), %.1f frames/s PNG in -> PNG out (plan creation included)\n", frames, g_used, frames / secs);
+        for (int rc : prc) if (rc) return rc > 0 ? rc : 1;
+        return 0;
+    }
     std::vector<std::thread> threads;
     std::vector<int> rcs(cfg.num_threads, 0);
     for (uint32_t t = 0; t < cfg.num_threads; ++t) {  // VkResample.cpp:1959-1969
