@@ -42,7 +42,7 @@ $(OUT)/libb2resample.so: $(OBJS)
 	$(NVCC) $(ARCH) -shared -o $@ $(OBJS) -ldl
 
 $(OUT)/b2resample: $(SRC)/cli.cpp $(OUT)/libb2resample.so include/b2resample.h
-	$(CXX) -std=c++17 -O2 -Iinclude $< -o $@ -L$(OUT) -lb2resample -lz -lpthread -Wl,-rpath,'$$ORIGIN'
+	$(CXX) -std=c++17 -O3 -Iinclude $< -o $@ -L$(OUT) -lb2resample -lz -lpthread -Wl,-rpath,'$$ORIGIN'
 
 emu:
 	tests/emu/build.sh

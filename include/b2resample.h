@@ -75,6 +75,12 @@ extern "C" {
  * together with B2R_FLAG_EXACT_SHARPEN it selects round 1's approximate-division variant of the exact kernels. */
 #define B2R_FLAG_FAST_SHARPEN 32u
 #define B2R_FLAG_EXACT_SHARPEN 64u
+/* Keep the C2R rows and the sharpen as two kernels with the pre-sharpen plane in HBM between them (the
+ * reference's tempBuffer round trip).  Default: ONE fused kernel per frame whenever the tolerance-bound sharpen
+ * applies and the row schedule is one of the built-in sizes -- same output bit for bit, ~200 MB less HBM
+ * traffic per 4096x2048 frame (csrc/b2r_fused.cuh).  (b2r_download_pre_sharpen on a fused plan rebuilds the
+ * plane with the stand-alone C2R kernel from the resident column spectra of the last frame.) */
+#define B2R_FLAG_SEPARATE_SHARPEN 128u
 
 typedef struct b2r_plan b2r_plan;
 
@@ -96,6 +102,8 @@ typedef struct b2r_plan_info {
     char jit_note[128];                /* why plan-time JIT was not used, "" otherwise                */
     uint32_t c2c_mode;                 /* 1 if created with B2R_FLAG_C2C_PARITY                   */
     size_t pre_sharpen_plane_stride;   /* elements between planes of the pre-sharpen buffer        */
+    uint32_t fused_strips_per_plane;   /* > 0: C2R rows + sharpen run as ONE kernel, this many strip CTAs per plane */
+    uint32_t sharpen_mode;             /* 0 exact kernels, 1 tolerance-bound kernels (b2r_cas.cuh)                 */
 } b2r_plan_info;
 
 /* devices_list(), VkResample.cpp:239-268; createInstance..createDevice, :1286-1320 */

@@ -16,7 +16,7 @@ def main():
         ms = min(p.execute(50) for _ in range(3))
         pk = p.profile_kernels(20)
         print(f"{w}x{h} p={prec}: {ms*1e3:.1f} us/frame = {1e3/ms:.0f} frames/s; static={p.info.static_kernels} "
-              f"cc={p.info.column_tile} sched={p.radix_schedule()}")
+              f"cc={p.info.column_tile} fused_nsp={p.info.fused_strips_per_plane} sched={p.radix_schedule()}")
         print("  per-kernel us:", {k: round(v * 1e3, 1) for k, v in pk.items()}, "sum", round(sum(pk.values()) * 1e3, 1))
 
 if __name__ == "__main__":

@@ -169,6 +169,28 @@ template <class P, int PPB> static void emu_c2r(FrameCtx& c, const P plan, const
     });
 }
 static int g_cols_grouped = 0;   // opt-in like the product (B2R_COLS_GROUPED=1)
+static int g_fused_nsp = 0;      // > 0: K7 + K8 through the fused strip kernel (b2r_fused.cuh) with this many strips per plane
+
+// fused C2R + sharpen + boundary fix-up, as launch_frame / run_fused do it (fp32, static schedules)
+template <class P> static void emu_fused(FrameCtx& c, const P plan, const HostFft& hf, void* out) {
+    const int nsp = g_fused_nsp, ppp = c.g.up_h / 2;
+    const float2* tw = hf.twiddles.data();
+    const float scale = 1.0f / (float)c.g.up_w;
+    const bool up2 = (c.g.up_w == 2 * c.g.w);
+    Dim3 grid, block; block.x = P::kT; grid.x = 3 * nsp;
+    b2r_emu::launch(grid, block, fused_smem_bytes(P::kN), [&] {
+        if (up2) k_c2r_sharpen_f32<P, true>(c.spec2.data(), (float*)out, (float*)c.pre.data(), tw, plan, c.dm, scale, nsp);
+        else k_c2r_sharpen_f32<P, false>(c.spec2.data(), (float*)out, (float*)c.pre.data(), tw, plan, c.dm, scale, nsp);
+    });
+    std::vector<int> fix;
+    for (int q = 1; q < nsp; ++q) {
+        const int b = 2 * fused_strip_begin(q, nsp, ppp);
+        fix.push_back((b - 2) | kFixCornerBit); fix.push_back(b - 1); fix.push_back(b);
+    }
+    fix.push_back((c.g.up_h - 2) | kFixCornerBit); fix.push_back(c.g.up_h - 1);
+    Dim3 g2, b2; b2.x = 32; g2.x = (c.g.up_w / 4 + 31) / 32; g2.y = (unsigned)fix.size(); g2.z = 3;
+    b2r_emu::launch(g2, b2, 0, [&] { k_sharpen_fix_f32<0>((const float*)c.pre.data(), (float*)out, c.dm, fix.data()); });
+}
 
 template <class PF, class PI, int CC>
 static void emu_cols(FrameCtx& c, const PF pf, const PI pi, const HostFft& hf, const HostFft& hi) {
@@ -217,6 +239,19 @@ static void emu_sharpen(const FrameDims dm, int precision, const void* pre, void
     });
 }
 
+static int g_sharpen_fast = 0;
+static void emu_sharpen_fast(const FrameDims dm, int precision, const void* pre, void* out) {
+    const int np = (precision == 2 || dm.up_w % 8 == 0) ? 8 : 4, ry = 12;
+    const int vecs = dm.up_w / np, bx = cas_fast_block(vecs);
+    Dim3 grid, block;
+    block.x = bx; grid.x = (vecs + bx - 1) / bx; grid.y = (dm.up_h + ry - 1) / ry; grid.z = 3;
+    b2r_emu::launch(grid, block, 0, [&] {
+        if (precision == 2) k_sharpen_fast_f16<8>((const __half*)pre, (__half*)out, dm, ry, 1);
+        else if (np == 8) k_sharpen_fast_f32<2>((const float*)pre, (float*)out, dm, ry, 1);
+        else k_sharpen_fast_f32<1>((const float*)pre, (float*)out, dm, ry, 1);
+    });
+}
+
 template <class P> static int emu_fft_static(int n, int dir, const float* in, float* out) {
     HostFft hf;
     Dim3 grid, block;
@@ -234,6 +269,8 @@ extern "C" {
 void b2r_emu_set_c2r_bulk(int on) { g_c2r_bulk = on; }
 void b2r_emu_set_c2c(int on) { g_c2c = on; }
 void b2r_emu_set_cols_grouped(int on) { g_cols_grouped = on; }
+void b2r_emu_set_fused(int nsp) { g_fused_nsp = nsp; }
+void b2r_emu_set_sharpen_fast(int on) { g_sharpen_fast = on; }
 
 // returns number of stages (>0) or -1; radices[] receives the schedule
 int b2r_emu_schedule(int n, int* radices, int* threads) {
@@ -322,7 +359,14 @@ int b2r_emu_frame(int w, int h, float upscale, int precision, float sharpen_cons
             else emu_cols<DynFft, DynFft, 2>(c, pf, pi, hf, hi);
         }
     }
-    {   // K7
+    bool fused_done = false;
+    if (g_fused_nsp > 0 && precision == 0 && use_static && !g_c2c) {   // K7 + K8 fused
+#define X(N, PPB, T, ...) \
+        if (!fused_done && g.up_w == N) { using P = StaticFft<N, T, __VA_ARGS__>; host_fft_of<P>(&hf); emu_fused<P>(c, P{}, hf, out); fused_done = true; used |= 4; }
+        B2R_STATIC_C2R_ROWS(X)
+#undef X
+    }
+    if (!fused_done) {   // K7
         bool done = false;
         if (use_static) {
 #define X(N, PPB, T, ...) \
@@ -335,8 +379,9 @@ int b2r_emu_frame(int w, int h, float upscale, int precision, float sharpen_cons
             emu_c2r<DynFft, 1>(c, DynFft{&hf.desc}, hf);
         }
     }
-    {   // K8
-        emu_sharpen(c.dm, precision, c.pre.data(), out);
+    if (!fused_done) {   // K8 (g_sharpen_fast: the tolerance-bound kernels, as the product's default)
+        if (g_sharpen_fast) emu_sharpen_fast(c.dm, precision, c.pre.data(), out);
+        else emu_sharpen(c.dm, precision, c.pre.data(), out);
     }
     if (used_static) *used_static = used;
     if (spec1_dump) memcpy(spec1_dump, c.spec1.data(), c.spec1.size() * sizeof(float2));

@@ -16,7 +16,7 @@ def lib():
         so = os.path.join(HERE, "emu", "libb2r_emu.so")
         srcs = [os.path.join(HERE, "emu", "emu.cpp")] + [
             os.path.join(HERE, "..", "vkresample_b200", "csrc", f)
-            for f in ("b2r_fft.cuh", "b2r_kernels.cuh", "b2r_cas.cuh", "b2r_plan.cpp", "b2r_plan.h", "b2r_common.cuh",
+            for f in ("b2r_fft.cuh", "b2r_kernels.cuh", "b2r_cas.cuh", "b2r_fused.cuh", "b2r_plan.cpp", "b2r_plan.h", "b2r_common.cuh",
                       "b2r_static_sizes.h")]
         if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
             subprocess.check_call([os.path.join(HERE, "emu", "build.sh")])
@@ -30,6 +30,8 @@ def lib():
         L.b2r_emu_sharpen_fast.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int, ctypes.c_float,
                                            ctypes.c_float, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                            ctypes.c_void_p, ctypes.c_void_p]
+        L.b2r_emu_set_fused.argtypes = [ctypes.c_int]
+        L.b2r_emu_set_sharpen_fast.argtypes = [ctypes.c_int]
         L.b2r_emu_u8_to_planar.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         L.b2r_emu_planar_to_u8.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         _LIB = L

@@ -315,3 +315,31 @@ def test_random_geometries():
         cc = int(rng.choice([2, 4, 8]))
         _check_frame(w, h, up, prec, 0.2, "noise" if done % 2 else "u8", cc=cc, use_static=False)
         done += 1
+
+
+@pytest.mark.parametrize("w,h,up,nsp", [(256, 128, 2.0, 1), (256, 128, 2.0, 5), (256, 128, 2.0, 42), (128, 64, 2.0, 3),
+                                        (512, 36, 1.0, 4), (256, 24, 2.0, 8)])
+def test_fused_c2r_sharpen_equals_separate_kernels(w, h, up, nsp):
+    """K7 + K8 as ONE kernel (b2r_fused.cuh: strip CTAs, rows kept in shared memory, boundary rows through the
+    pre-sharpen buffer + k_sharpen_fix) against the separate C2R + tolerance-bound sharpen kernels: the same
+    bytes, for one strip per plane, many strips, the smallest strips (3 pairs), up == 1 (no x zero padding:
+    the generic first-stage operand pattern) and planes whose last row's corner reads the next plane"""
+    plan = vo.make_plan(w, h, up)
+    x = vo.synthetic_frame("noise", w, h, 3)
+    L = eu.lib()
+    L.b2r_emu_set_sharpen_fast(1)
+    try:
+        L.b2r_emu_set_fused(0)
+        sep = eu.frame(x, up, 0, 0.2, plan)
+        L.b2r_emu_set_fused(nsp)
+        fus = eu.frame(x, up, 0, 0.2, plan)
+    finally:
+        L.b2r_emu_set_fused(0)
+        L.b2r_emu_set_sharpen_fast(0)
+    assert sep["used_static"] & 4 and fus["used_static"] & 4
+    assert np.isfinite(fus["out"]).all()
+    bad = np.argwhere(sep["out"].view(np.uint32) != fus["out"].view(np.uint32))
+    assert bad.size == 0, (len(bad), bad[:10])
+    # and the separate default path itself is within tolerance of the oracle
+    ref = vo.sharpen(sep["pre"], plan, 0.2, 0)
+    assert np.abs(sep["out"].astype(np.float64) - ref.astype(np.float64)).max() <= 1e-5

@@ -24,10 +24,11 @@ TOL_E2E_FP16 = 1e-2
 TOL_SHARPEN = {0: 1e-5, 2: 1e-2}     # default (tolerance-bound) sharpen vs oracle.sharpen on the identical plane
 
 
-def fast_sharpen_applies(up_w, prec, s):
-    """mirror of sharpen_fast_applies (csrc/b2r_sharpen.cu)"""
+def fast_sharpen_applies(up_w, up_h, prec, s):
+    """mirror of sharpen_fast_applies (csrc/b2r_sharpen.cu): constant in [0, 0.24], 16-byte aligned rows and planes"""
     s32 = float(np.float32("%f" % np.float32(s)))
-    return prec != 1 and 0.0 <= s32 <= 0.24 and up_w % (8 if prec == 2 else 4) == 0
+    v = 8 if prec == 2 else 4
+    return prec != 1 and 0.0 <= s32 <= 0.24 and up_w % v == 0 and ((up_w + 2) * up_h) % v == 0
 WORKERS = os.cpu_count()
 
 
@@ -69,7 +70,7 @@ def _check(w, h, up, prec, s, kind, expect_static=None, e2e_tol=None, flags=0, e
     # default plan: same plane bit for bit, sharpen within tolerance of the oracle on that plane
     _, _, out, pre_d, sh_only, _ = _run(w, h, up, prec, s, kind, flags=flags)
     assert _same_bits(pre, pre_d), "pre-sharpen plane depends on the sharpen flag"
-    if fast_sharpen_applies(plan_o.up_w, prec, s):
+    if fast_sharpen_applies(plan_o.up_w, plan_o.up_h, prec, s):
         ok = np.isfinite(sh_o.astype(np.float64))
         e_sh = max(float(np.abs(out.astype(np.float64) - sh_o.astype(np.float64))[ok].max()),
                    float(np.abs(sh_only.astype(np.float64) - sh_o.astype(np.float64))[ok].max()))

@@ -29,6 +29,7 @@ FLAG_JIT = 8
 FLAG_NO_JIT = 16
 FLAG_FAST_SHARPEN = 32   # round-1 opt-in, now a no-op on its own (the default sharpen is the tolerance-bound one)
 FLAG_EXACT_SHARPEN = 64  # bit-exact (oracle-identical) sharpen kernels, see b2resample.h
+FLAG_SEPARATE_SHARPEN = 128  # C2R rows and sharpen as two kernels (default: one fused kernel where it applies)
 
 # every symbol include/b2resample.h declares (checked by tests/test_abi.py)
 EXPORTS = [
@@ -60,6 +61,7 @@ class PlanInfo(ctypes.Structure):
         ("column_tile", ctypes.c_uint32), ("kernels_per_frame", ctypes.c_uint32), ("static_kernels", ctypes.c_uint32),
         ("jit_kernels", ctypes.c_uint32), ("jit_note", ctypes.c_char * 128),
         ("c2c_mode", ctypes.c_uint32), ("pre_sharpen_plane_stride", ctypes.c_size_t),
+        ("fused_strips_per_plane", ctypes.c_uint32), ("sharpen_mode", ctypes.c_uint32),
     ]
 
 

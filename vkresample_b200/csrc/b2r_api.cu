@@ -107,6 +107,10 @@ struct b2r_plan {
     int kernels_per_frame = 4;
     unsigned char* u8_in0 = nullptr;   // lane 0's u8 staging
     unsigned char* u8_out0 = nullptr;
+    // fused C2R + sharpen (b2r_fused.cuh): strips per plane, fix-up list (device), 0 = separate kernels
+    int fused_nsp = 0;
+    int* d_fix = nullptr;
+    int n_fix = 0;
     JitModule* jit = nullptr;   // kernels compiled at plan time for sizes without an ahead-of-time build
     std::string jit_note;       // why JIT was not used (if it was not)
     std::vector<Lane> extra;   // lanes 1..n-1
@@ -154,6 +158,13 @@ int launch_frame(b2r_plan* p, cudaStream_t s, const void* d_in = nullptr, void* 
     ColsArgs a2{spec1, spec2, p->tw_h, p->tw_uh, p->d_fd + 1, p->d_fd + 2, p->dm, 1.0f / (float)g.up_h, nyq};
     CU(p->k_cols.launch(s, a2, p->k_cols.inv.threads, p->k_cols.smem, p->k_cols.ctx));
     if (ev) CU(cudaEventRecord(ev[2], s));
+    if (p->fused_nsp > 0) {   // K7 + K8 in one kernel; the boundary rows go through the pre-sharpen buffer
+        FusedArgs af{spec2, d_out ? d_out : (ln ? ln->d_out : p->d_out), pre, p->tw_uw, p->dm, g.precision,
+                     1.0f / (float)g.up_w, p->fused_nsp, p->d_fix, p->n_fix};
+        CU(p->k_c2r.fused(s, af));
+        if (ev) { CU(cudaEventRecord(ev[3], s)); CU(cudaEventRecord(ev[4], s)); }
+        return B2R_SUCCESS;
+    }
     C2rArgs a3{spec2, pre, p->tw_uw, p->d_fd + 3, p->dm, g.precision, 1.0f / (float)g.up_w, nyq};
     if (p->c2c) CU(p->k_c2r.c2c(s, a3, p->k_c2r.sched.threads, p->k_c2r.smem_c2c, p->k_c2r.ctx));
     else CU(p->k_c2r.c2r(s, a3, p->k_c2r.sched.threads, p->k_c2r.smem, p->k_c2r.ctx));
@@ -348,6 +359,26 @@ int build(b2r_plan* p) {
     d.up2_d = raw ? (double)g.up2 : literal_d(g.up2);
     d.sharpen_d = raw ? (double)g.sharpen : literal_d(g.sharpen);
 
+    // ---- fused C2R + sharpen: whenever the tolerance-bound sharpen applies and the row schedule is built in
+    // (B2R_FUSED=0 / B2R_FLAG_SEPARATE_SHARPEN keep the two kernels; B2R_FUSED_NSP overrides the strip count)
+    {
+        SharpenArgs sa{nullptr, nullptr, p->dm, g.precision};
+        sa.exact = (p->flags & B2R_FLAG_EXACT_SHARPEN) != 0;
+        const int ppp = g.up_h / 2;
+        const bool want = !(p->flags & B2R_FLAG_SEPARATE_SHARPEN) && env_int("B2R_FUSED", 1) != 0;
+        if (want && !p->c2c && g.precision == 0 && sharpen_fast_applies(sa) && p->k_c2r.fused && !p->k_c2r.is_jit &&
+            ppp >= 6 && fused_smem_bytes(g.up_w) <= smem_max && p->k_c2r.prepare_fused(g.precision) == cudaSuccess) {
+            const int per_sm = p->k_c2r.fused_blocks_per_sm(g.precision);
+            if (per_sm >= 1) {
+                const int slots = prop.multiProcessorCount * per_sm;
+                int nsp = env_int("B2R_FUSED_NSP", 0);
+                if (nsp <= 0) nsp = std::max(1, slots / 3);          // one wave of strip CTAs over the three planes
+                nsp = std::min(nsp, ppp / 3);                         // at least 3 pairs per strip
+                p->fused_nsp = std::max(1, nsp);
+            }
+        }
+    }
+
     // device memory
     const size_t eb = g.elem_bytes();
     const size_t b_in = g.input_bytes(), b_pre = g.pre_elems * eb, b_out = g.output_bytes();
@@ -386,6 +417,22 @@ int build(b2r_plan* p) {
     if ((rc = put(p->fw, &p->tw_w)) || (rc = put(p->fh, &p->tw_h)) || (rc = put(p->fuh, &p->tw_uh)) ||
         (rc = put(p->fuw, &p->tw_uw)))
         return rc;
+
+    if (p->fused_nsp > 0) {   // rows k_sharpen_fix finishes, per plane (b2r_fused.cuh)
+        std::vector<int> fix;
+        const int ppp = g.up_h / 2, nsp = p->fused_nsp;
+        for (int q = 1; q < nsp; ++q) {
+            const int b = 2 * fused_strip_begin(q, nsp, ppp);        // first row of strip q
+            fix.push_back((b - 2) | kFixCornerBit);
+            fix.push_back(b - 1);
+            fix.push_back(b);
+        }
+        fix.push_back((g.up_h - 2) | kFixCornerBit);                 // plane end: the row below is the pad region
+        fix.push_back(g.up_h - 1);
+        p->n_fix = (int)fix.size();
+        CU(cudaMalloc((void**)&p->d_fix, fix.size() * sizeof(int)));
+        CU(cudaMemcpy(p->d_fix, fix.data(), fix.size() * sizeof(int), cudaMemcpyHostToDevice));
+    }
 
     CU(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&p->ev0));
@@ -473,6 +520,7 @@ void b2r_plan_destroy(b2r_plan* p) {
     if (p->stream) cudaStreamDestroy(p->stream);
     cudaFree(p->d_in); cudaFree(p->d_pre); cudaFree(p->d_out);
     cudaFree(p->d_spec1); cudaFree(p->d_spec2); cudaFree(p->d_tw); cudaFree(p->d_fd); cudaFree(p->d_nyq);
+    cudaFree(p->d_fix);
     delete p;
 }
 
@@ -503,6 +551,12 @@ int b2r_plan_get_info(const b2r_plan* p, b2r_plan_info* info) {
     info->jit_kernels = (p->k_r2c.is_jit ? 1u : 0u) | (p->k_cols.is_jit ? 2u : 0u) | (p->k_c2r.is_jit ? 4u : 0u);
     snprintf(info->jit_note, sizeof info->jit_note, "%s", p->jit_note.c_str());
     info->kernels_per_frame = p->kernels_per_frame;
+    info->fused_strips_per_plane = (uint32_t)p->fused_nsp;
+    {
+        SharpenArgs sa{nullptr, nullptr, p->dm, g.precision};
+        sa.exact = (p->flags & B2R_FLAG_EXACT_SHARPEN) != 0;
+        info->sharpen_mode = p->c2c ? (sa.exact ? 0u : (sharpen_fast_applies(sa) ? 1u : 0u)) : (sharpen_fast_applies(sa) ? 1u : 0u);
+    }
     return B2R_SUCCESS;
 }
 
@@ -567,6 +621,13 @@ uint64_t b2r_plan_launch_count(const b2r_plan* p) { return p ? p->launches : 0; 
 int b2r_download_pre_sharpen(b2r_plan* p, void* host_out) {
     if (!p || !host_out) return fail(B2R_ERR_INVALID_ARG, "null argument");
     CU(cudaSetDevice(p->device));
+    if (p->fused_nsp > 0) {
+        // a fused plan never holds the whole plane: rebuild it with the stand-alone C2R kernel from the column
+        // spectra of the last frame, which are still resident (same arithmetic, same values)
+        C2rArgs a3{p->d_spec2, p->d_pre, p->tw_uw, p->d_fd + 3, p->dm, p->g.precision, 1.0f / (float)p->g.up_w, nullptr};
+        CU(p->k_c2r.c2r(p->stream, a3, p->k_c2r.sched.threads, p->k_c2r.smem, p->k_c2r.ctx));
+        p->launches += 1;
+    }
     CU(cudaMemcpyAsync(host_out, p->d_pre, b2r_plan_pre_sharpen_bytes(p), cudaMemcpyDeviceToHost, p->stream));
     CU(cudaStreamSynchronize(p->stream));
     return B2R_SUCCESS;
@@ -742,7 +803,7 @@ int b2r_wait_ticket(b2r_plan* p, uint64_t ticket) {
 
 void* b2r_host_alloc(size_t bytes) {
     void* ptr = nullptr;
-    if (cudaHostAlloc(&ptr, bytes, cudaHostAllocDefault) != cudaSuccess) {
+    if (cudaHostAlloc(&ptr, bytes, cudaHostAllocPortable) != cudaSuccess) {
         fail(B2R_ERR_NOMEM, "cudaHostAlloc(%zu) failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
         return nullptr;
     }

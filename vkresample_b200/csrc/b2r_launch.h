@@ -33,6 +33,13 @@ struct SharpenArgs {
     int reverse = -1;      // fast kernels: walk planes / strips against K7's write order (-1: default)
 };
 
+struct FusedArgs {     // K7 + K8 in one kernel (b2r_fused.cuh) followed by the boundary-row fix-up
+    const float2* spec; void* out; void* pre; const float2* tw; FrameDims dm; int precision; float scale;
+    int nsp;               // strips per colour plane (one CTA per strip)
+    const int* fix_list;   // device: rows / last pixels k_sharpen_fix finishes (per plane)
+    int n_fix;
+};
+
 struct Schedule {      // radix list + cooperating threads of one transform
     int n = 0, nst = 0, threads = 0;
     int radices[kMaxStages] = {};
@@ -53,6 +60,10 @@ struct RowImpl {       // K1 or K7 resolved for one size
     cudaError_t (*prepare_c2c)(size_t smem, const void* ctx) = nullptr;
     int ppb_c2c = 1;
     size_t smem_c2c = 0;
+    // fused C2R + sharpen (static schedules, fp32 / fp16): nullptr when not instantiated
+    cudaError_t (*prepare_fused)(int precision) = nullptr;
+    int (*fused_blocks_per_sm)(int precision) = nullptr;       // resident CTAs per SM (occupancy API)
+    cudaError_t (*fused)(cudaStream_t, const FusedArgs&) = nullptr;
 };
 
 struct ColImpl {       // fused column kernel resolved for one (H, upH) pair
@@ -84,6 +95,7 @@ void get_dynamic_cols_cc2(ColImpl* out);
 void get_dynamic_cols_cc4(ColImpl* out);
 void get_dynamic_cols_cc8(ColImpl* out);
 
+cudaError_t launch_sharpen_fix(cudaStream_t s, const FusedArgs& a);   // boundary rows of the fused kernel
 cudaError_t launch_sharpen_kernel(cudaStream_t s, const SharpenArgs& a);
 bool sharpen_fast_applies(const SharpenArgs& a);   // true: the tolerance-bound kernels (b2r_cas.cuh) will run
 cudaError_t launch_u8_to_planar(cudaStream_t s, const unsigned char* src, void* dst, const FrameDims& dm, int precision);

@@ -18,7 +18,9 @@ int env_or(const char* name, int dflt) {
 bool sharpen_fast_applies(const SharpenArgs& a) {
     if (a.exact || a.precision == 1) return false;
     if (!(a.dm.sharpen >= 0.0f && a.dm.sharpen <= kCasFastMaxSharpen)) return false;
-    return a.precision == 2 ? (a.dm.up_w % 8 == 0) : (a.dm.up_w % 4 == 0);
+    // 16-byte vector accesses: rows and planes must start on 16-byte boundaries
+    if (a.precision == 2) return a.dm.up_w % 8 == 0 && a.dm.pre_plane % 8 == 0 && a.dm.out_plane % 8 == 0;
+    return a.dm.up_w % 4 == 0 && a.dm.pre_plane % 4 == 0 && a.dm.out_plane % 4 == 0;
 }
 
 static cudaError_t launch_sharpen_fast(cudaStream_t s, const SharpenArgs& a) {
@@ -36,6 +38,15 @@ static cudaError_t launch_sharpen_fast(cudaStream_t s, const SharpenArgs& a) {
         k_sharpen_fast_f32<2><<<grid, block, 0, s>>>((const float*)a.pre, (float*)a.out, a.dm, ry, reverse);
     else
         k_sharpen_fast_f32<1><<<grid, block, 0, s>>>((const float*)a.pre, (float*)a.out, a.dm, ry, reverse);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sharpen_fix(cudaStream_t s, const FusedArgs& a) {
+    if (a.n_fix <= 0) return cudaSuccess;
+    if (a.precision != 0) return cudaErrorNotSupported;
+    const int groups = a.dm.up_w / 4, bx = 128;
+    dim3 block(bx), grid((groups + bx - 1) / bx, a.n_fix, 3);
+    k_sharpen_fix_f32<0><<<grid, block, 0, s>>>((const float*)a.pre, (float*)a.out, a.dm, a.fix_list);
     return cudaGetLastError();
 }
 

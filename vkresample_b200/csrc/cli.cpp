@@ -114,17 +114,27 @@ static bool load_rgb_impl(const char* path, std::vector<unsigned char>* rgb, int
     for (int y = 0; y < height; ++y) {
         const unsigned char* row = &raw[(stride + 1) * y];
         const int ft = row[0];
-        for (size_t i = 0; i < stride; ++i) {
-            int a = i >= bpp ? cur[i - bpp] : 0, b = prev[i], c = i >= bpp ? prev[i - bpp] : 0, x = row[1 + i];
-            switch (ft) {
-                case 0: break;
-                case 1: x += a; break;
-                case 2: x += b; break;
-                case 3: x += (a + b) >> 1; break;
-                case 4: x += paeth(a, b, c); break;
-                default: *err = "bad PNG filter"; return false;
-            }
-            cur[i] = (unsigned char)x;
+        const unsigned char* in = row + 1;
+        unsigned char* c = cur.data();
+        const unsigned char* pr = prev.data();
+        switch (ft) {   // one tight loop per filter type (the first bpp bytes have no left neighbour)
+            case 0: memcpy(c, in, stride); break;
+            case 1:
+                for (size_t i = 0; i < bpp && i < stride; ++i) c[i] = in[i];
+                for (size_t i = bpp; i < stride; ++i) c[i] = (unsigned char)(in[i] + c[i - bpp]);
+                break;
+            case 2:
+                for (size_t i = 0; i < stride; ++i) c[i] = (unsigned char)(in[i] + pr[i]);
+                break;
+            case 3:
+                for (size_t i = 0; i < bpp && i < stride; ++i) c[i] = (unsigned char)(in[i] + (pr[i] >> 1));
+                for (size_t i = bpp; i < stride; ++i) c[i] = (unsigned char)(in[i] + ((c[i - bpp] + pr[i]) >> 1));
+                break;
+            case 4:
+                for (size_t i = 0; i < bpp && i < stride; ++i) c[i] = (unsigned char)(in[i] + pr[i]);
+                for (size_t i = bpp; i < stride; ++i) c[i] = (unsigned char)(in[i] + paeth(c[i - bpp], pr[i], pr[i - bpp]));
+                break;
+            default: *err = "bad PNG filter"; return false;
         }
         unsigned char* out = pix + (size_t)y * width * 3;
         for (int x = 0; x < width; ++x) {
@@ -159,28 +169,65 @@ static bool load_rgb(const char* path, std::vector<unsigned char>* rgb, int* w, 
     }
 }
 
+// width / height from the IHDR chunk alone (the pipelined batch mode sizes its pinned ring before decoding anything)
+static bool read_size(const char* path, int* w, int* h, std::string* err) {
+    FILE* f = fopen(path, "rb");
+    if (!f) { *err = "cannot open file"; return false; }
+    unsigned char b[33];
+    const size_t n = fread(b, 1, sizeof b, f);
+    fclose(f);
+    static const unsigned char sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    if (n < 33 || memcmp(b, sig, 8) || be32(b + 8) != 13 || memcmp(b + 12, "IHDR", 4)) { *err = "not a PNG file"; return false; }
+    const uint32_t uw = be32(b + 16), uh = be32(b + 20);
+    if (uw == 0 || uh == 0 || uw >= 65536u || uh >= 65536u) { *err = "image dimensions out of range (1..65535)"; return false; }
+    *w = (int)uw; *h = (int)uh;
+    return true;
+}
+
 // 8-bit RGB encoder with per-row adaptive filtering (minimum sum of absolute differences)
 static int g_zlevel = 6;   // -pnglevel
 static bool write_rgb(const char* path, const unsigned char* rgb, int w, int h) {
     const size_t stride = (size_t)w * 3;
     std::vector<unsigned char> raw((stride + 1) * h), cand(stride), best(stride);
     std::vector<unsigned char> zero(stride, 0);
+    // candidate rows in tight, branch-free loops (auto-vectorised); cost = sum |signed residual| (the usual heuristic)
+    auto cost_of = [&](const unsigned char* r) { long c = 0; for (size_t i = 0; i < stride; ++i) c += std::abs((int)(signed char)r[i]); return c; };
     for (int y = 0; y < h; ++y) {
         const unsigned char* cur = rgb + stride * y;
         const unsigned char* prev = y ? rgb + stride * (y - 1) : zero.data();
+        unsigned char* dst = &raw[(stride + 1) * y];
+        if (g_zlevel == 0) { dst[0] = 0; memcpy(dst + 1, cur, stride); continue; }   // stored: filtering buys nothing
         long best_cost = -1; int best_ft = 0;
         for (int ft = 0; ft < 5; ++ft) {
-            long cost = 0;
-            for (size_t i = 0; i < stride; ++i) {
-                int a = i >= 3 ? cur[i - 3] : 0, b = prev[i], c = i >= 3 ? prev[i - 3] : 0, x = cur[i];
-                int v = ft == 0 ? x : ft == 1 ? x - a : ft == 2 ? x - b : ft == 3 ? x - ((a + b) >> 1) : x - paeth(a, b, c);
-                cand[i] = (unsigned char)v;
-                cost += std::abs((int)(signed char)cand[i]);
+            unsigned char* o = cand.data();
+            switch (ft) {
+                case 0: memcpy(o, cur, stride); break;
+                case 1:
+                    o[0] = cur[0]; o[1] = cur[1]; o[2] = cur[2];
+                    for (size_t i = 3; i < stride; ++i) o[i] = (unsigned char)(cur[i] - cur[i - 3]);
+                    break;
+                case 2:
+                    for (size_t i = 0; i < stride; ++i) o[i] = (unsigned char)(cur[i] - prev[i]);
+                    break;
+                case 3:
+                    for (size_t i = 0; i < 3; ++i) o[i] = (unsigned char)(cur[i] - (prev[i] >> 1));
+                    for (size_t i = 3; i < stride; ++i) o[i] = (unsigned char)(cur[i] - ((cur[i - 3] + prev[i]) >> 1));
+                    break;
+                default:
+                    for (size_t i = 0; i < 3; ++i) o[i] = (unsigned char)(cur[i] - prev[i]);
+                    for (size_t i = 3; i < stride; ++i) {
+                        const int a = cur[i - 3], b = prev[i], c = prev[i - 3];
+                        const int pa = std::abs(b - c), pb = std::abs(a - c), pc = std::abs(a + b - 2 * c);
+                        const int pred = (pa <= pb && pa <= pc) ? a : (pb <= pc ? b : c);
+                        o[i] = (unsigned char)(cur[i] - pred);
+                    }
+                    break;
             }
+            const long cost = cost_of(o);
             if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_ft = ft; best.swap(cand); }
         }
-        raw[(stride + 1) * y] = (unsigned char)best_ft;
-        memcpy(&raw[(stride + 1) * y + 1], best.data(), stride);
+        dst[0] = (unsigned char)best_ft;
+        memcpy(dst + 1, best.data(), stride);
     }
     uLongf zlen = compressBound(raw.size());
     std::vector<unsigned char> z(zlen);
@@ -398,42 +445,52 @@ struct Pipeline {
         }
     }
 
+    // plan creation runs on the submitting thread while the codec workers already decode into the ring
+    int create_plan() {
+        int rc = b2r_plan_create(&plan, device, (uint32_t)w, (uint32_t)h, cfg.upscale, cfg.precision, cfg.sharpen, plan_flags(cfg));
+        if (rc) { printf("Plan creation failed, error code: %d (%s)\n", rc, b2r_last_error()); return rc; }
+        const uint32_t lanes = std::max(1u, std::min(cfg.lanes, 8u));
+        if ((rc = b2r_plan_set_lanes(plan, lanes))) { printf("set_lanes failed: %s\n", b2r_last_error()); return rc; }
+        b2r_plan_info pi;
+        b2r_plan_get_info(plan, &pi);
+        if (pi.up_w != info.up_w || pi.up_h != info.up_h) { printf("internal error: output size mismatch\n"); return -1; }
+        plan_notices(cfg, pi);
+        if (gpu_index == 0)
+            printf("VRAM per GPU: %d MB (%u lanes), %u codec threads + 1 submit thread per GPU\n", (int)(pi.device_bytes >> 20), lanes, cfg.num_threads);
+        std::lock_guard<std::mutex> g(mu);
+        info = pi;
+        return 0;
+    }
+
     int run() {
         const int ndev = b2r_device_count();
         if (ndev < 1) { printf("No CUDA device found: %s\n", b2r_last_error()); return -1; }
         device = (int)((cfg.device_id + (uint32_t)gpu_index) % (uint32_t)ndev);
         char name[512];
         snprintf(name, sizeof name, "%s/%06u.png", cfg.ifolder, file_of(0));
-        std::vector<unsigned char> probe;
         std::string err;
-        if (!png::load_rgb(name, &probe, &w, &h, &err)) { printf("Image not found (%s: %s)\n", name, err.c_str()); return 5; }
-        int rc = b2r_plan_create(&plan, device, (uint32_t)w, (uint32_t)h, cfg.upscale, cfg.precision, cfg.sharpen, plan_flags(cfg));
-        if (rc) { printf("Plan creation failed, error code: %d (%s)\n", rc, b2r_last_error()); return rc; }
-        b2r_plan_get_info(plan, &info);
-        plan_notices(cfg, info);
+        if (!png::read_size(name, &w, &h, &err)) { printf("Image not found (%s: %s)\n", name, err.c_str()); return 5; }
+        // output size as the reference computes it (VkResample.cpp:1417-1418); checked against the plan's once it exists
+        info.up_w = (uint32_t)(cfg.upscale * (float)w); info.up_h = (uint32_t)(cfg.upscale * (float)h);
         const uint32_t lanes = std::max(1u, std::min(cfg.lanes, 8u));
-        if ((rc = b2r_plan_set_lanes(plan, lanes))) { printf("set_lanes failed: %s\n", b2r_last_error()); return rc; }
-        b2r_plan_get_info(plan, &info);
-        if (gpu_index == 0)
-            printf("VRAM per GPU: %d MB (%u lanes), %u codec threads + 1 submit thread per GPU\n", (int)(info.device_bytes >> 20), lanes, cfg.num_threads);
         const size_t n_slots = std::min<size_t>(total, (size_t)cfg.num_threads + 2 * lanes + 2);
         slots.resize(n_slots);
         for (auto& s : slots) {
-            s.in = (unsigned char*)b2r_host_alloc(b2r_plan_input_u8_bytes(plan));
-            s.out = (unsigned char*)b2r_host_alloc(b2r_plan_output_u8_bytes(plan));
+            s.in = (unsigned char*)b2r_host_alloc((size_t)3 * w * h);
+            s.out = (unsigned char*)b2r_host_alloc((size_t)3 * info.up_w * info.up_h);
             if (!s.in || !s.out) { printf("pinned allocation failed: %s\n", b2r_last_error()); return -4; }
         }
         std::vector<std::thread> th;
-        th.emplace_back([this] { submit_loop(); });
+        th.emplace_back([this] { int rc = create_plan(); if (rc) fail_with(rc); else submit_loop(); });
         for (uint32_t t = 0; t < cfg.num_threads; ++t) th.emplace_back([this] { worker_loop(); });
         for (auto& t : th) t.join();
-        b2r_synchronize(plan);
+        if (plan) b2r_synchronize(plan);
         for (auto& s : slots) { b2r_host_free(s.in); b2r_host_free(s.out); }
         char dev_name[256] = "";
         b2r_device_name(device, dev_name, sizeof dev_name);
         printf("GPU %d finished: %u frames, codec thread-seconds: decode %.2f, encode %.2f, waiting for the GPU %.2f. Device name: %s API:%s\n",
                gpu_index, written, t_decode, t_encode, t_wait, dev_name, b2r_version());
-        b2r_plan_destroy(plan);
+        if (plan) b2r_plan_destroy(plan);
         return error;
     }
 };
@@ -467,6 +524,7 @@ int main(int argc, char* argv[]) {
                "\t-pnglevel X: (extension) zlib level of the PNG encoder, 0..9 (default 6)\n");
         return 0;
     }
+    if (char* lv = flag_value(argv, argv + argc, "-pnglevel")) { int z = atoi(lv); if (z >= 0 && z <= 9) png::g_zlevel = z; }
     if (find_flag(argv, argv + argc, "-pngcopy")) {  // diagnostic: decode + re-encode (codec self-test, no GPU)
         char* in = flag_value(argv, argv + argc, "-pngcopy");
         char* out = flag_value(argv, argv + argc, "-o");
