@@ -368,7 +368,7 @@ def run_b200(args):
     # ---- roofline of the dominant kernel (separate pass, events between kernels, same workload)
     pk = plan.profile_kernels(20)
     alg = kernel_algorithmic_bytes(w, h, plan.up_w, plan.up_h, elem)
-    if pk.get("sharpen", 0.0) == 0.0 and "c2r_rows" in pk:   # fused C2R + sharpen: one kernel, no pre-sharpen plane
+    if int(plan.info.fused_strips_per_plane) > 0:   # fused C2R + sharpen (+ boundary-row fix-up): no pre-sharpen plane
         pk = {"r2c_rows": pk["r2c_rows"], "cols": pk["cols"], "c2r_sharpen": pk["c2r_rows"]}
         alg["c2r_sharpen"] = alg["c2r_rows"]   # S2 in + output once (the pre-sharpen plane never reaches HBM)
     dom = max(pk, key=pk.get)
@@ -409,6 +409,7 @@ def run_b200(args):
                            "radix_schedule": plan.radix_schedule(), "column_tile": int(plan.info.column_tile),
                            "static_kernels": int(plan.info.static_kernels),
                            "kernels_per_frame": int(plan.info.kernels_per_frame),
+                           "fused_c2r_sharpen_strips_per_plane": int(plan.info.fused_strips_per_plane),
                            "cpu_affinity": affinity,
                            "sharpen_arithmetic": "correctly rounded, bit-identical to the oracle (B2R_FLAG_EXACT_SHARPEN)" if args.exact_sharpen
                                                  else "tolerance-bound (default): within 1e-5 fp32 / 1e-2 fp16 of oracle.sharpen on the same plane"},

@@ -178,7 +178,7 @@ template <class P> static void emu_fused(FrameCtx& c, const P plan, const HostFf
     const float scale = 1.0f / (float)c.g.up_w;
     const bool up2 = (c.g.up_w == 2 * c.g.w);
     Dim3 grid, block; block.x = P::kT; grid.x = 3 * nsp;
-    b2r_emu::launch(grid, block, fused_smem_bytes(P::kN), [&] {
+    b2r_emu::launch(grid, block, fused_smem_bytes(P::kN, c.g.nx), [&] {
         if (up2) k_c2r_sharpen_f32<P, true>(c.spec2.data(), (float*)out, (float*)c.pre.data(), tw, plan, c.dm, scale, nsp);
         else k_c2r_sharpen_f32<P, false>(c.spec2.data(), (float*)out, (float*)c.pre.data(), tw, plan, c.dm, scale, nsp);
     });

@@ -366,10 +366,15 @@ int build(b2r_plan* p) {
         sa.exact = (p->flags & B2R_FLAG_EXACT_SHARPEN) != 0;
         const int ppp = g.up_h / 2;
         const bool want = !(p->flags & B2R_FLAG_SEPARATE_SHARPEN) && env_int("B2R_FUSED", 1) != 0;
-        if (want && !p->c2c && g.precision == 0 && sharpen_fast_applies(sa) && p->k_c2r.fused && !p->k_c2r.is_jit &&
-            ppp >= 6 && fused_smem_bytes(g.up_w) <= smem_max && p->k_c2r.prepare_fused(g.precision) == cudaSuccess) {
-            const int per_sm = p->k_c2r.fused_blocks_per_sm(g.precision);
-            if (per_sm >= 1) {
+        bool ok = want && !p->c2c && g.precision == 0 && sharpen_fast_applies(sa) && p->k_c2r.fused && !p->k_c2r.is_jit &&
+                  ppp >= 6 && fused_smem_bytes(g.up_w, g.nx) <= smem_max;
+        if (ok && p->k_c2r.prepare_fused(g.precision, g.nx) != cudaSuccess) { (void)cudaGetLastError(); ok = false; }
+        if (ok) {
+            // measured on B200 (profiles/): the fused kernel wins while two strip CTAs fit one SM (4096- and 3840-wide
+            // rows: +5 % sustained, half the HBM traffic, no power-cap throttling); with a single resident CTA
+            // (7680-wide rows) the separate kernels are faster (307 vs 349 us).  B2R_FUSED=2 forces it.
+            const int per_sm = p->k_c2r.fused_blocks_per_sm(g.precision, g.nx);
+            if (per_sm >= 2 || (per_sm >= 1 && env_int("B2R_FUSED", 1) == 2)) {
                 const int slots = prop.multiProcessorCount * per_sm;
                 int nsp = env_int("B2R_FUSED_NSP", 0);
                 if (nsp <= 0) nsp = std::max(1, slots / 3);          // one wave of strip CTAs over the three planes

@@ -25,35 +25,61 @@ namespace b2r {
 
 // ---- strip geometry (host and device agree through these) -----------------------------------------
 B2R_HD int fused_strip_begin(int q, int nsp, int pairs_per_plane) { return (int)(((long long)q * pairs_per_plane) / nsp); }
-// shared memory of one CTA: two workspaces, each a multiple of 16 bytes (the rows are read as 16-byte vectors)
+// shared memory of one CTA: [2 mbarriers | staging 0 | staging 1 | workspace 0 | workspace 1].  A staging
+// buffer holds the two spectrum rows of one pair (bulk-copied one pair ahead, like k_c2r_rows_bulk); the
+// workspaces are multiples of 16 bytes (the rows they end up holding are read as 16-byte vectors).
 B2R_HD constexpr int fused_ws_len(int n) { return (smem_padded_len(n) + 1) & ~1; }
-B2R_HD constexpr size_t fused_smem_bytes(int n) { return 2 * (size_t)fused_ws_len(n) * sizeof(real2); }
+B2R_HD constexpr size_t fused_smem_bytes(int n, int nx) {
+    return 16 + 4 * (size_t)c2r_stage_row_elems(nx) * sizeof(real2) + 2 * (size_t)fused_ws_len(n) * sizeof(real2);
+}
 // fix-up list entry: output row y, or only its last pixel
 constexpr int kFixCornerBit = 1 << 30;
-// register budget: 168 per thread (two radix-16 butterflies in flight in the FFT phase, the 4 x 6 tap window
-// in the sharpen phase) -- three 128-thread CTAs per SM
-constexpr int fused_min_blocks(int threads) {
-    int b = 65536 / (168 * threads);
-    return b < 1 ? 1 : b;
+// register budget per thread: 128 with one butterfly per thread in every stage (two 256-thread CTAs per SM),
+// 168 when a thread holds more than 16 complex values
+template <class P> constexpr int fused_min_blocks() {
+    const int regs = (P::max_elems() > 16) ? 168 : 128;
+    const int b = 65536 / (regs * P::kT);
+    return b < 1 ? 1 : (b > 6 ? 6 : b);
 }
 
 #if !defined(B2R_REAL_IS_DOUBLE)
 
-// One group of NP pixels of rows `up`, `mid`, `dn` held in shared memory as clamped magnitudes.
-// right_* : the element that follows the row's last one in flat order (used when x0 + NP == n).
-template <int NP>
-B2R_DEV void fused_taps_f32(const float* row, int x0, int n, float right_end, float (&t)[NP + 2]) {
-#pragma unroll
-    for (int k = 0; k < NP / 4; ++k) {
-        const float4 v = *reinterpret_cast<const float4*>(row + x0 + 4 * k);
-        t[4 * k + 1] = v.x; t[4 * k + 2] = v.y; t[4 * k + 3] = v.z; t[4 * k + 4] = v.w;
+// Clamped magnitudes of columns x0-1 .. x0+3 of one row held in shared memory, given the row's four own values
+// `v` (loaded ahead of time).  right_end: the element that follows the row's last one in flat order (used when
+// x0 + 4 == n).  SHFL: the halo columns come from the neighbouring lanes -- a scalar shared load with a 16-byte
+// lane stride is a 4-way bank conflict -- which needs every lane of a full warp to take part; otherwise (CTAs
+// that are not a multiple of 32 threads, and the CPU emulator) they are loaded.
+template <bool SHFL>
+B2R_DEV void fused_taps4(const float* row, const float4 v, int x0, int n, float right_end, float (&t)[6]) {
+    t[1] = v.x; t[2] = v.y; t[3] = v.z; t[4] = v.w;
+#if !defined(B2R_HOST_EMU)
+    if constexpr (SHFL) {
+        const int lane = (int)B2R_TID_X & 31;
+        float l = __shfl_up_sync(0xffffffffu, v.w, 1);
+        float r = __shfl_down_sync(0xffffffffu, v.x, 1);
+        if (lane == 0) l = row[x0 > 0 ? x0 - 1 : 0];             // left clamps at 0
+        if (lane == 31) r = row[x0 + 4 < n ? x0 + 4 : x0];
+        t[0] = l;
+        t[5] = (x0 + 4 < n) ? r : right_end;                     // right does not clamp: flat +1
+        return;
     }
-    t[0] = (x0 > 0) ? row[x0 - 1] : t[1];                       // left clamps at 0
-    t[NP + 1] = (x0 + NP < n) ? row[x0 + NP] : right_end;       // right does not clamp: flat +1
+#endif
+    t[0] = row[x0 > 0 ? x0 - 1 : 0];
+    t[5] = (x0 + 4 < n) ? row[x0 + 4] : right_end;
 }
 
+// thread count of the fused kernel per row length: one butterfly per thread in the widest stage (twice the
+// warps of the stand-alone C2R schedules, which run two butterflies per thread: the sharpen phase needs
+// the extra warps to cover its MUFU / shared-memory latencies; measured in profiles/)
+template <class P> struct FusedSchedule { using type = P; };
+template <> struct FusedSchedule<StaticFft<4096, 128, 16, 16, 16>> { using type = StaticFft<4096, 256, 16, 16, 16>; };
+template <> struct FusedSchedule<StaticFft<3840, 128, 16, 16, 15>> { using type = StaticFft<3840, 256, 16, 16, 15>; };
+template <> struct FusedSchedule<StaticFft<7680, 384, 16, 20, 24>> { using type = StaticFft<7680, 512, 16, 20, 24>; };
+template <> struct FusedSchedule<StaticFft<5120, 160, 20, 16, 16>> { using type = StaticFft<5120, 320, 20, 16, 16>; };
+template <> struct FusedSchedule<StaticFft<2560, 128, 16, 16, 10>> { using type = StaticFft<2560, 256, 16, 16, 10>; };
+
 template <class P, bool UP2>
-B2R_KERNEL B2R_LAUNCH_BOUNDS((row_launch_bound<P, 1>()), (fused_min_blocks(row_launch_bound<P, 1>())))
+B2R_KERNEL B2R_LAUNCH_BOUNDS((P::kT), (fused_min_blocks<P>()))
 k_c2r_sharpen_f32(const real2* __restrict__ spec, float* __restrict__ out, float* __restrict__ pre,
                   const real2* __restrict__ tw, const P plan, const FrameDims dm, const real scale, const int nsp) {
     constexpr int NP = 4;
@@ -63,7 +89,11 @@ k_c2r_sharpen_f32(const real2* __restrict__ spec, float* __restrict__ out, float
     const int j0 = fused_strip_begin(q, nsp, ppp), j1 = fused_strip_begin(q + 1, nsp, ppp);
     const int S = j1 - j0;
     const bool top = (j0 == 0);
-    real2* const ws0 = B2R_SMEM(real2);
+    const int row_elems = c2r_stage_row_elems(dm.nx);
+    unsigned char* const smem_base = B2R_SMEM(unsigned char);
+    unsigned long long* const bar = reinterpret_cast<unsigned long long*>(smem_base);
+    real2* const stg = reinterpret_cast<real2*>(smem_base + 16);
+    real2* const ws0 = stg + 4 * (size_t)row_elems;
     const int ws_len = fused_ws_len(n);
     const float up2 = dm.up2, neg_s = -dm.sharpen;
     const real2* sp = spec + (size_t)c * dm.up_h * dm.spec_stride;
@@ -83,8 +113,36 @@ k_c2r_sharpen_f32(const real2* __restrict__ spec, float* __restrict__ out, float
 #endif
     };
 
+    // producer side (thread 0): both spectrum rows of pair `pj` -> staging buffer `buf` (cp.async.bulk + mbarrier)
+    auto issue = [&](int pj, int buf) {
+        const real2* src = sp + (size_t)(2 * pj) * dm.spec_stride;
+        real2* dst = stg + (size_t)buf * 2 * row_elems;
+#if defined(B2R_HOST_EMU)
+        for (int e = 0; e < row_elems; ++e) { dst[e] = src[e]; dst[row_elems + e] = src[dm.spec_stride + e]; }
+#else
+        const unsigned bytes = (unsigned)(row_elems * sizeof(real2));
+        b2r_mbar_expect_tx(&bar[buf], 2 * bytes);
+        b2r_bulk_g2s(dst, src, bytes, &bar[buf]);
+        b2r_bulk_g2s(dst + row_elems, src + dm.spec_stride, bytes, &bar[buf]);
+#endif
+    };
+#if !defined(B2R_HOST_EMU)
+    if (tid == 0) { b2r_mbar_init(&bar[0], 1); b2r_mbar_init(&bar[1], 1); b2r_mbar_fence_init(); }
+    B2R_SYNC();
+#endif
+    if (tid == 0) issue(j0, 0);
+
     for (int i = 0; i < S; ++i) {
         const int j = j0 + i;
+        // the next pair's rows travel while this pair is transformed and sharpened; its staging buffer was last
+        // read by the first FFT stage of pair i-1, two CTA barriers ago
+        if (tid == 0 && i + 1 < S) issue(j + 1, (i + 1) & 1);
+#if defined(B2R_HOST_EMU)
+        B2R_SYNC();
+#else
+        b2r_mbar_wait(&bar[i & 1], (unsigned)((i >> 1) & 1));
+#endif
+        const real2* const sa = stg + (size_t)(i & 1) * 2 * row_elems;
         real2* const wsc = ws0 + (i & 1) * ws_len;
         float* cur = reinterpret_cast<float*>(wsc);                 // rows 2j (cur[0..n)) and 2j+1 (cur[n..2n))
         const float* prv = reinterpret_cast<const float*>(ws0 + ((i & 1) ^ 1) * ws_len);   // rows 2j-2, 2j-1
@@ -93,8 +151,7 @@ k_c2r_sharpen_f32(const real2* __restrict__ spec, float* __restrict__ out, float
         const bool head = (i == 1), tail = (i == S - 2);
         float* p0 = pplane + (size_t)(2 * j) * n;
         float* p1 = p0 + n;
-        const real2* a = sp + (size_t)(2 * j) * dm.spec_stride;
-        c2r_pair_emit<P, UP2, false, true>(plan, a, a + dm.spec_stride, wsc, tw, dm, tid, true, [&](int idx, real2 z) {
+        c2r_pair_emit<P, UP2, true, true>(plan, sa, sa + row_elems, wsc, tw, dm, tid, true, [&](int idx, real2 z) {
             const float v0 = z.x * scale, v1 = z.y * scale;
             cur[idx] = cas_tap(up2, v0);
             cur[n + idx] = cas_tap(up2, v1);
@@ -105,45 +162,63 @@ k_c2r_sharpen_f32(const real2* __restrict__ spec, float* __restrict__ out, float
             }
         });
         B2R_SYNC();
+        constexpr bool kShfl = (P::kT % 32 == 0);
+        constexpr int K = (P::kN / NP + P::kT - 1) / P::kT;      // pixel groups per thread and row
+        const float* rowa = prv;          // row 2j-2
+        const float* rowb = prv + n;      // row 2j-1
+        const float* rowc = cur;          // row 2j
+        const float* rowd = cur + n;      // row 2j+1
+        auto ld4 = [&](const float* row, int x0) { return *reinterpret_cast<const float4*>(row + x0); };
+        auto x_of = [&](int k) { const int g = k * T + tid; return (g < G ? g : g_last) * NP; };   // lanes past the row end re-read the last group
         if (i == 0) {
             if (top) {   // row 0 of the plane: the row above clamps to row 0 itself
-                for (int g = tid; g < G; g += T) {
-                    const int x0 = g * NP;
+#pragma unroll 1
+                for (int k = 0; k < K; ++k) {     // every lane runs every trip (warp shuffles inside)
+                    const bool valid = k * T + tid < G;
+                    const int x0 = x_of(k);
                     float tc[NP + 2], td[NP + 2], o[NP];
-                    fused_taps_f32<NP>(cur, x0, n, cur[n], tc);          // row 0; after its end comes row 1
-                    fused_taps_f32<NP>(cur + n, x0, n, 0.f, td);         // row 1; its right end (row 2) is not here yet
+                    fused_taps4<kShfl>(rowc, ld4(rowc, x0), x0, n, rowc[n], tc);   // row 0; after its end comes row 1
+                    fused_taps4<kShfl>(rowd, ld4(rowd, x0), x0, n, 0.f, td);       // row 1; its right end (row 2) is not here yet
                     cas_row_f32<NP>(tc, tc, td, neg_s, o);
-                    store4(oplane + x0, o);
-                    if (g == g_last) { corner_up0 = tc[NP - 1]; corner_up1 = tc[NP]; }
+                    if (valid) store4(oplane + x0, o);
                 }
                 corner_pending = true;
+                if (tid == g_last % T) { corner_up0 = rowc[n - 2]; corner_up1 = rowc[n - 1]; }
             }
         } else {
             const int ya = 2 * j - 1, yb = 2 * j;
-            for (int g = tid; g < G; g += T) {
-                const int x0 = g * NP;
+            const float end_a = rowa[n], end_b = rowc[0], end_c = rowc[n];   // the elements after each row's end (flat order)
+            // the four rows of the NEXT group are loaded before the current group is computed
+            float4 va = ld4(rowa, x_of(0)), vb = ld4(rowb, x_of(0)), vc = ld4(rowc, x_of(0)), vd = ld4(rowd, x_of(0));
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const bool valid = k * T + tid < G;
+                const int x0 = x_of(k);
+                float4 na = va, nb = vb, nc = vc, nd = vd;
+                if (k + 1 < K) { const int x1 = x_of(k + 1); na = ld4(rowa, x1); nb = ld4(rowb, x1); nc = ld4(rowc, x1); nd = ld4(rowd, x1); }
                 float ta[NP + 2], tb[NP + 2], tc[NP + 2], td[NP + 2], o[NP];
-                fused_taps_f32<NP>(prv, x0, n, prv[n], ta);              // row 2j-2, then row 2j-1
-                fused_taps_f32<NP>(prv + n, x0, n, cur[0], tb);          // row 2j-1, then row 2j (other slot)
-                fused_taps_f32<NP>(cur, x0, n, cur[n], tc);              // row 2j, then row 2j+1
-                fused_taps_f32<NP>(cur + n, x0, n, 0.f, td);             // row 2j+1; row 2j+2 comes with the next pair
+                fused_taps4<kShfl>(rowa, va, x0, n, end_a, ta);
+                fused_taps4<kShfl>(rowb, vb, x0, n, end_b, tb);
+                fused_taps4<kShfl>(rowc, vc, x0, n, end_c, tc);
+                fused_taps4<kShfl>(rowd, vd, x0, n, 0.f, td);                // row 2j+2 comes with the next pair
                 cas_row_f32<NP>(ta, tb, tc, neg_s, o);
-                store4(oplane + (size_t)ya * n + x0, o);
+                if (valid) store4(oplane + (size_t)ya * n + x0, o);
                 cas_row_f32<NP>(tb, tc, td, neg_s, o);
-                store4(oplane + (size_t)yb * n + x0, o);                 // its last pixel is redone one pair later
-                if (g == g_last) {
-                    if (corner_pending) {   // pixel (n-1, 2j-2): rows 2j-3 (registers), 2j-2, 2j-1, and row 2j's first tap
-                        // the tap after the upper row's end: row 2j-2's first one -- or, for plane row 0 (whose
-                        // upper row clamps to row 0 itself), row 1's
-                        float up3[3] = {corner_up0, corner_up1, (yb - 2 == 0) ? prv[n] : prv[0]};
-                        float mid3[3] = {ta[NP - 1], ta[NP], prv[n]};
-                        float dn3[3] = {tb[NP - 1], tb[NP], cur[0]};
-                        float o1[1];
-                        cas_row_f32<1>(up3, mid3, dn3, neg_s, o1);
-                        oplane[(size_t)(yb - 2) * n + n - 1] = o1[0];
-                    }
-                    corner_up0 = tb[NP - 1]; corner_up1 = tb[NP];
+                if (valid) store4(oplane + (size_t)yb * n + x0, o);          // its last pixel is redone one pair later
+                va = na; vb = nb; vc = nc; vd = nd;
+            }
+            if (tid == g_last % T) {   // the thread that owns the rows' last pixel group
+                if (corner_pending) {  // pixel (n-1, 2j-2): rows 2j-3 (registers), 2j-2, 2j-1, and row 2j's first tap
+                    // the tap after the upper row's end: row 2j-2's first one -- or, for plane row 0 (whose
+                    // upper row clamps to row 0 itself), row 1's
+                    float up3[3] = {corner_up0, corner_up1, (yb - 2 == 0) ? rowa[n] : rowa[0]};
+                    float mid3[3] = {rowa[n - 2], rowa[n - 1], rowa[n]};
+                    float dn3[3] = {rowb[n - 2], rowb[n - 1], rowc[0]};
+                    float o1[1];
+                    cas_row_f32<1>(up3, mid3, dn3, neg_s, o1);
+                    oplane[(size_t)(yb - 2) * n + n - 1] = o1[0];
                 }
+                corner_up0 = rowb[n - 2]; corner_up1 = rowb[n - 1];
             }
             corner_pending = true;
         }

@@ -61,8 +61,8 @@ struct RowImpl {       // K1 or K7 resolved for one size
     int ppb_c2c = 1;
     size_t smem_c2c = 0;
     // fused C2R + sharpen (static schedules, fp32 / fp16): nullptr when not instantiated
-    cudaError_t (*prepare_fused)(int precision) = nullptr;
-    int (*fused_blocks_per_sm)(int precision) = nullptr;       // resident CTAs per SM (occupancy API)
+    cudaError_t (*prepare_fused)(int precision, int nx) = nullptr;
+    int (*fused_blocks_per_sm)(int precision, int nx) = nullptr;   // resident CTAs per SM (occupancy API)
     cudaError_t (*fused)(cudaStream_t, const FusedArgs&) = nullptr;
 };
 

@@ -79,23 +79,23 @@ template <class P, int PPB> cudaError_t run_c2c(cudaStream_t s, const C2rArgs& a
 }
 
 // ---- fused C2R + sharpen (b2r_fused.cuh): one CTA per strip of row pairs -----------------------------
-template <class P> cudaError_t prep_fused(int precision) {
+template <class P> cudaError_t prep_fused(int precision, int nx) {
     if (precision != 0) return cudaErrorNotSupported;
-    const int n = (int)fused_smem_bytes(P::kN);
+    const int n = (int)fused_smem_bytes(P::kN, nx);
     cudaError_t e;
     if ((e = cudaFuncSetAttribute(k_c2r_sharpen_f32<P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, n))) return e;
     return cudaFuncSetAttribute(k_c2r_sharpen_f32<P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, n);
 }
-template <class P> int fused_per_sm(int precision) {
+template <class P> int fused_per_sm(int precision, int nx) {
     if (precision != 0) return 0;
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_c2r_sharpen_f32<P, true>, P::kT, fused_smem_bytes(P::kN)) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_c2r_sharpen_f32<P, true>, P::kT, fused_smem_bytes(P::kN, nx)) != cudaSuccess) return 0;
     return per_sm;
 }
 template <class P> cudaError_t run_fused(cudaStream_t s, const FusedArgs& a) {
     if (a.precision != 0) return cudaErrorNotSupported;
     const bool up2 = (a.dm.up_w == 2 * a.dm.w);
-    const size_t smem = fused_smem_bytes(P::kN);
+    const size_t smem = fused_smem_bytes(P::kN, a.dm.nx);
     const int grid = 3 * a.nsp;
     if (up2) k_c2r_sharpen_f32<P, true><<<grid, P::kT, smem, s>>>(a.spec, (float*)a.out, (float*)a.pre, a.tw, P{}, a.dm, a.scale, a.nsp);
     else k_c2r_sharpen_f32<P, false><<<grid, P::kT, smem, s>>>(a.spec, (float*)a.out, (float*)a.pre, a.tw, P{}, a.dm, a.scale, a.nsp);
@@ -118,9 +118,10 @@ template <class P, int PPB> void fill(RowImpl* o, const char* name) {
     o->ppb_c2c = PPB;
     o->smem_c2c = o->smem;
     if constexpr (P::kStages >= 2 && P::kN % 8 == 0) {
-        o->prepare_fused = &prep_fused<P>;
-        o->fused_blocks_per_sm = &fused_per_sm<P>;
-        o->fused = &run_fused<P>;
+        using PF = typename FusedSchedule<P>::type;   // same radix list (same twiddle table), its own thread count
+        o->prepare_fused = &prep_fused<PF>;
+        o->fused_blocks_per_sm = &fused_per_sm<PF>;
+        o->fused = &run_fused<PF>;
     }
     // default: the bulk-copy (mbarrier-prefetched, persistent) kernel; B2R_C2R_BULK=0 selects the
     // direct-load kernel.  Measured on B200, c2: 44.4 -> 39.1 us stand-alone (profiles/README.md).
