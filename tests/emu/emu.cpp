@@ -111,8 +111,22 @@ struct FrameCtx {
     std::vector<unsigned char> pre;
 };
 
+static int g_r2c_bulk = 0;   // emulate the bulk-copy (persistent) K1 instead of the direct-load one
+
 template <class P, int PPB> static void emu_r2c(FrameCtx& c, const P plan, const HostFft& hf) {
     int pairs = 3 * c.g.h / 2;
+    if (g_r2c_bulk) {
+        if constexpr (P::kStatic) {
+            Dim3 grid, block; block.x = hf.desc.threads; grid.x = 7;   // few persistent CTAs, many trips
+            const float2* tw = hf.twiddles.data();
+            const size_t elem = c.precision == 2 ? 2 : 4;
+            b2r_emu::launch(grid, block, r2c_bulk_smem_bytes(P::kN, elem), [&] {
+                if (c.precision == 2) k_r2c_rows_bulk<P, __half>((const __half*)c.in, c.spec1.data(), tw, plan, c.dm, pairs);
+                else k_r2c_rows_bulk<P, float>((const float*)c.in, c.spec1.data(), tw, plan, c.dm, pairs);
+            });
+            return;
+        }
+    }
     Dim3 grid, block; block.x = hf.desc.threads; block.y = PPB; grid.x = (pairs + PPB - 1) / PPB;
     const float2* tw = hf.twiddles.data();
     b2r_emu::launch(grid, block, PPB * smem_padded_len(c.g.w) * sizeof(float2), [&] {
@@ -267,6 +281,7 @@ template <class P> static int emu_fft_static(int n, int dir, const float* in, fl
 extern "C" {
 
 void b2r_emu_set_c2r_bulk(int on) { g_c2r_bulk = on; }
+void b2r_emu_set_r2c_bulk(int on) { g_r2c_bulk = on; }
 void b2r_emu_set_c2c(int on) { g_c2c = on; }
 void b2r_emu_set_cols_grouped(int on) { g_cols_grouped = on; }
 void b2r_emu_set_fused(int nsp) { g_fused_nsp = nsp; }

@@ -343,3 +343,21 @@ def test_fused_c2r_sharpen_equals_separate_kernels(w, h, up, nsp):
     # and the separate default path itself is within tolerance of the oracle
     ref = vo.sharpen(sep["pre"], plan, 0.2, 0)
     assert np.abs(sep["out"].astype(np.float64) - ref.astype(np.float64)).max() <= 1e-5
+
+
+@pytest.mark.parametrize("w,h,prec", [(256, 16, 0), (512, 12, 2), (640, 8, 0)])
+def test_r2c_bulk_kernel_equals_direct_kernel(w, h, prec):
+    """K1 with the row pairs staged by bulk copies (persistent CTAs, several trips each) writes the same row
+    spectra, bit for bit, as the one-pair-per-CTA kernel that loads straight from global memory"""
+    plan = vo.make_plan(w, h, 2.0)
+    x = vo.synthetic_frame("noise", w, h, 9)
+    L = eu.lib()
+    a = eu.frame(x, 2.0, prec, 0.2, plan)
+    L.b2r_emu_set_r2c_bulk(1)
+    try:
+        b = eu.frame(x, 2.0, prec, 0.2, plan)
+    finally:
+        L.b2r_emu_set_r2c_bulk(0)
+    assert a["used_static"] & 1 and b["used_static"] & 1
+    assert np.array_equal(a["spec1"].view(np.uint64), b["spec1"].view(np.uint64))
+    assert np.array_equal(a["out"].view(np.uint8), b["out"].view(np.uint8))
