@@ -33,7 +33,7 @@ def frame_of(f, w, h):
 
 def compare(a, b):
     da, db = json.load(open(a)), json.load(open(b))
-    assert da["frames"] == db["frames"] and da["config"] == db["config"], "different streams"
+    assert da["frames"] == db["frames"] and da["config"].split(", frame f")[0] == db["config"].split(", frame f")[0], "different streams"
     bad = [f for f in da["digests"] if da["digests"][f] != db["digests"].get(f)]
     print(json.dumps({"compare": [a, b], "frames": da["frames"], "world": [da["world"], db["world"]],
                       "byte_identical_frames": da["frames"] - len(bad), "mismatching_frames": bad[:8]}))

@@ -50,7 +50,7 @@ def main():
         m = re.search(r"Total time: ([0-9.]+) s", r.stdout)
         total = float(m.group(1)) if m else dt
         res[mode] = {"frames_per_s": args.frames / total, "total_s": total, "wall_s": dt,
-                     "stdout_tail": [l for l in r.stdout.splitlines() if "finished" in l or "Pipelined" in l][-9:]}
+                     "stdout_tail": [l for l in r.stdout.splitlines() if "finished" in l or "Pipelined" in l or "timeline" in l][-17:]}
         n_out = len([f for f in os.listdir(od) if f.endswith(".png")])
         res[mode]["files_written"] = n_out
     shutil.rmtree(tmp, ignore_errors=True)

@@ -474,3 +474,91 @@ def test_random_sizes_factors_precisions(tmp_path):
     print(r.stdout[-3000:])
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-1000:]
     assert "10 cases, 0 failures" in r.stdout
+
+
+def test_lanes_grow_and_shrink():
+    """b2r_plan_set_lanes really changes the lane count both ways and frames stay identical"""
+    x = vo.synthetic_frame("noise", 512, 256, 4)
+    with vb.Plan(512, 256) as p:
+        ref = p.upscale(x).copy()
+        bytes1 = int(p.get_info().device_bytes)
+        p.set_lanes(4)
+        assert p.lanes == 4 and int(p.get_info().device_bytes) > bytes1
+        p.set_lanes(1)
+        assert p.lanes == 1
+        assert int(p.get_info().device_bytes) == bytes1    # the extra lanes' memory was released
+        assert np.array_equal(ref, p.upscale(x))
+        p.set_lanes(2)
+        import torch
+        h_in = torch.from_numpy(p.pack_input(x)).pin_memory()
+        h_out = [torch.empty((3, p.up_h, p.up_w), dtype=torch.float32).pin_memory() for _ in range(4)]
+        tickets = []
+        for o in h_out:
+            p.enqueue_host(h_in.data_ptr(), o.data_ptr())
+            tickets.append(p.last_ticket)
+        assert tickets == sorted(tickets) and len(set(tickets)) == 4
+        for t, o in zip(tickets, h_out):                   # per-frame completion (b2r_wait_ticket)
+            p.wait_ticket(t)
+            assert np.array_equal(ref, o.numpy())
+
+
+def test_jit_cache_is_private_and_self_healing(tmp_path, monkeypatch):
+    """a truncated cubin in the cache is deleted and recompiled; a cache directory other users can
+    write to is not used at all; without any private directory plans still build (no caching)"""
+    import stat
+    w, h = 1000, 600      # no ahead-of-time schedule -> plan-time JIT
+    x = vo.synthetic_frame("noise", w, h).astype(np.float32)
+    cache = tmp_path / "cache"
+    monkeypatch.setenv("B2R_CACHE_DIR", str(cache))
+    with vb.Plan(w, h) as p:
+        assert p.info.jit_kernels == 7
+        ref = p.upscale(x).copy()
+    assert stat.S_IMODE(os.stat(cache).st_mode) & 0o077 == 0                 # created 0700
+    cubins = [f for f in os.listdir(cache) if f.endswith(".cubin")]
+    assert cubins
+    for f in cubins:                                                         # corrupt every cached cubin
+        with open(cache / f, "r+b") as fh:
+            fh.truncate(1000)
+    with vb.Plan(w, h) as p:                                                 # rejected by the driver -> recompiled
+        assert p.info.jit_kernels == 7
+        assert np.array_equal(ref, p.upscale(x))
+    assert all(os.path.getsize(cache / f) > 1000 for f in os.listdir(cache) if f.endswith(".cubin"))
+    shared = tmp_path / "shared"
+    shared.mkdir()
+    os.chmod(shared, 0o777)                                                  # writable by others: never trusted
+    monkeypatch.setenv("B2R_CACHE_DIR", str(shared))
+    with vb.Plan(w, h) as p:
+        assert p.info.jit_kernels == 7 and np.array_equal(ref, p.upscale(x))
+    assert os.listdir(shared) == []
+    monkeypatch.delenv("B2R_CACHE_DIR")
+    monkeypatch.delenv("HOME", raising=False)                                # no private directory at all
+    with vb.Plan(w, h) as p:
+        assert p.info.jit_kernels == 7 and np.array_equal(ref, p.upscale(x))
+
+
+def test_forced_jit_without_nvrtc_is_an_error(monkeypatch):
+    """B2R_FORCE_JIT seeds schedules the any-size kernels cannot run; a failing JIT must not fall
+    back silently"""
+    monkeypatch.setenv("B2R_FORCE_JIT", "1")
+    monkeypatch.setenv("B2R_JIT", "0")
+    with pytest.raises(vb.B2RError) as e:
+        vb.Plan(1024, 512)
+    assert "B2R_FORCE_JIT" in str(e.value)
+
+
+def test_stream_sharding_is_deterministic_across_gpu_counts(tmp_path):
+    """SURVEY 8e on hardware: frame f of a stream gives the same bytes whether 1 GPU or every GPU of the box
+    processes the stream (scripts/c4_stream.py, frame f -> rank (f-1) mod N).  Needs >= 2 GPUs."""
+    import subprocess, sys, json
+    n = vb.device_count()
+    if n < 2:
+        pytest.skip("needs at least two GPUs")
+    n = min(n, 8)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    a, b = str(tmp_path / "n1.json"), str(tmp_path / "nN.json")
+    common = [os.path.join(root, "scripts", "c4_stream.py"), "--frames", "24"]
+    subprocess.run([sys.executable] + common + ["--out", a], check=True, cwd=root, timeout=900)
+    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
+                    "--master-port", "29533"] + common + ["--out", b], check=True, cwd=root, timeout=900)
+    da, db = json.load(open(a)), json.load(open(b))
+    assert db["world"] == n and da["digests"] == db["digests"] and len(da["digests"]) == 24

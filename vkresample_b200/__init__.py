@@ -172,6 +172,12 @@ class Plan:
         self.input_bytes, self.output_bytes = info.input_bytes, info.output_bytes
         self.device = device
 
+    def get_info(self) -> "PlanInfo":
+        """a fresh b2r_plan_get_info snapshot (``self.info`` is the one taken at creation)"""
+        info = PlanInfo()
+        _check(self._lib.b2r_plan_get_info(self._h, ctypes.byref(info)))
+        return info
+
     # -- layouts -----------------------------------------------------------------------------
     @property
     def in_plane_stride(self) -> int:

@@ -45,6 +45,21 @@ int fail(int code, const char* fmt, ...) {
             return fail(B2R_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
     } while (0)
 
+// Entry points run on the plan's device and leave the caller's current device as they found it.
+struct DeviceGuard {
+    int prev = -1;
+    bool good = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != dev) good = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    bool ok() const { return good; }
+};
+#define ON_PLAN_DEVICE(p)                                                                           \
+    DeviceGuard b2r_guard_((p)->device);                                                            \
+    if (!b2r_guard_.ok()) return fail(B2R_ERR_CUDA, "cudaSetDevice(%d) failed", (p)->device)
+
 float literal_f(float v) {  // value of the "%f" text the reference pastes into its GLSL (VkResample.cpp:893-920)
     char t[64];
     snprintf(t, sizeof t, "%f", (double)v);
@@ -327,6 +342,10 @@ int build(b2r_plan* p) {
         } else {
             p->jit_note = why;
         }
+        // B2R_FORCE_JIT seeds the descriptors with the ahead-of-time schedules (two butterflies per thread, ...),
+        // which the any-size kernels cannot run: without the JIT build there is nothing valid to fall back to
+        if (force_jit && !(p->k_r2c.is_jit && p->k_cols.is_jit && p->k_c2r.is_jit))
+            return fail(B2R_ERR_UNSUPPORTED, "B2R_FORCE_JIT: plan-time JIT failed (%s)", p->jit_note.c_str());
     }
     if (dbl && !(p->k_r2c.is_jit && p->k_cols.is_jit && p->k_c2r.is_jit))
         return fail(B2R_ERR_UNSUPPORTED, "precision 1 (double) needs the plan-time JIT: %s", p->jit_note.c_str());
@@ -492,7 +511,8 @@ int b2r_plan_create(b2r_plan** out, int device, uint32_t w, uint32_t h, float up
         return fail(B2R_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
                     e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
     if (device < 0 || device >= ndev) return fail(B2R_ERR_INVALID_ARG, "device %d out of range [0,%d)", device, ndev);
-    CU(cudaSetDevice(device));
+    DeviceGuard guard(device);   // the caller's current device is restored on return
+    if (!guard.ok()) return fail(B2R_ERR_CUDA, "cudaSetDevice(%d) failed", device);
     b2r_plan* p = new (std::nothrow) b2r_plan();
     if (!p) return fail(B2R_ERR_NOMEM, "out of host memory");
     p->device = device; p->flags = flags; p->g = g; p->c2c = c2c;
@@ -504,7 +524,7 @@ int b2r_plan_create(b2r_plan** out, int device, uint32_t w, uint32_t h, float up
 
 void b2r_plan_destroy(b2r_plan* p) {
     if (!p) return;
-    cudaSetDevice(p->device);
+    DeviceGuard guard(p->device);
     if (p->stream) cudaStreamSynchronize(p->stream);
     for (Lane& l : p->extra) {
         if (l.stream) { cudaStreamSynchronize(l.stream); cudaStreamDestroy(l.stream); }
@@ -544,9 +564,11 @@ int b2r_plan_get_info(const b2r_plan* p, b2r_plan_info* info) {
     info->input_bytes = g.input_bytes(); info->output_bytes = g.output_bytes();
     info->device_bytes = p->device_bytes;
     const HostFft* f[4] = {&p->fw, &p->fh, &p->fuh, &p->fuw};
+    // thread counts of the kernels that actually launch (the JIT chooser may halve the seed's counts)
+    const int launched[4] = {p->k_r2c.sched.threads, p->k_cols.fwd.threads, p->k_cols.inv.threads, p->k_c2r.sched.threads};
     for (int i = 0; i < 4; ++i) {
         info->n_stages[i] = f[i]->desc.nstages;
-        info->threads[i] = f[i]->desc.threads;
+        info->threads[i] = launched[i] > 0 ? launched[i] : f[i]->desc.threads;
         for (int s = 0; s < f[i]->desc.nstages; ++s) info->radices[i][s] = f[i]->desc.st[s].radix;
     }
     info->c2c_mode = p->c2c ? 1u : 0u;
@@ -567,7 +589,7 @@ int b2r_plan_get_info(const b2r_plan* p, b2r_plan_info* info) {
 
 int b2r_upload(b2r_plan* p, const void* host_in) {
     if (!p || !host_in) return fail(B2R_ERR_INVALID_ARG, "null argument");
-    CU(cudaSetDevice(p->device));
+    ON_PLAN_DEVICE(p);
     CU(cudaMemcpyAsync(p->d_in, host_in, p->g.input_bytes(), cudaMemcpyHostToDevice, p->stream));
     CU(cudaStreamSynchronize(p->stream));
     return B2R_SUCCESS;
@@ -575,7 +597,7 @@ int b2r_upload(b2r_plan* p, const void* host_in) {
 
 int b2r_execute(b2r_plan* p, uint32_t num_iter, double* ms_per_iter) {
     if (!p || num_iter == 0) return fail(B2R_ERR_INVALID_ARG, "null plan or num_iter == 0");
-    CU(cudaSetDevice(p->device));
+    ON_PLAN_DEVICE(p);
     CU(cudaEventRecord(p->ev0, p->stream));
     for (uint32_t i = 0; i < num_iter; ++i) {
         int rc = run_frame(p);
@@ -594,7 +616,7 @@ int b2r_execute(b2r_plan* p, uint32_t num_iter, double* ms_per_iter) {
 
 int b2r_download(b2r_plan* p, void* host_out) {
     if (!p || !host_out) return fail(B2R_ERR_INVALID_ARG, "null argument");
-    CU(cudaSetDevice(p->device));
+    ON_PLAN_DEVICE(p);
     CU(cudaMemcpyAsync(host_out, p->d_out, p->g.output_bytes(), cudaMemcpyDeviceToHost, p->stream));
     CU(cudaStreamSynchronize(p->stream));
     return B2R_SUCCESS;
@@ -602,7 +624,7 @@ int b2r_download(b2r_plan* p, void* host_out) {
 
 int b2r_upscale_host(b2r_plan* p, const void* host_in, void* host_out, double* ms_total) {
     if (!p || !host_in || !host_out) return fail(B2R_ERR_INVALID_ARG, "null argument");
-    CU(cudaSetDevice(p->device));
+    ON_PLAN_DEVICE(p);
     CU(cudaEventRecord(p->ev0, p->stream));
     CU(cudaMemcpyAsync(p->d_in, host_in, p->g.input_bytes(), cudaMemcpyHostToDevice, p->stream));
     int rc = run_frame(p);
@@ -625,7 +647,7 @@ uint64_t b2r_plan_launch_count(const b2r_plan* p) { return p ? p->launches : 0; 
 
 int b2r_download_pre_sharpen(b2r_plan* p, void* host_out) {
     if (!p || !host_out) return fail(B2R_ERR_INVALID_ARG, "null argument");
-    CU(cudaSetDevice(p->device));
+    ON_PLAN_DEVICE(p);
     if (p->fused_nsp > 0) {
         // a fused plan never holds the whole plane: rebuild it with the stand-alone C2R kernel from the column
         // spectra of the last frame, which are still resident (same arithmetic, same values)
@@ -640,7 +662,7 @@ int b2r_download_pre_sharpen(b2r_plan* p, void* host_out) {
 
 int b2r_sharpen_host(b2r_plan* p, const void* host_pre, void* host_out) {
     if (!p || !host_pre || !host_out) return fail(B2R_ERR_INVALID_ARG, "null argument");
-    CU(cudaSetDevice(p->device));
+    ON_PLAN_DEVICE(p);
     CU(cudaMemcpyAsync(p->d_pre, host_pre, b2r_plan_pre_sharpen_bytes(p), cudaMemcpyHostToDevice, p->stream));
     int rc = launch_sharpen(p, p->stream);
     if (rc) return rc;
@@ -650,20 +672,28 @@ int b2r_sharpen_host(b2r_plan* p, const void* host_pre, void* host_out) {
     return B2R_SUCCESS;
 }
 
-int b2r_plan_set_lanes(b2r_plan* p, uint32_t lanes) {
-    if (!p || lanes < 1 || lanes > 8) return fail(B2R_ERR_INVALID_ARG, "lanes must be in [1, 8]");
-    CU(cudaSetDevice(p->device));
-    CU(cudaStreamSynchronize(p->stream));
+namespace {
+void free_lane(Lane& l) {
+    if (l.stream) { cudaStreamSynchronize(l.stream); cudaStreamDestroy(l.stream); }
+    if (l.done) cudaEventDestroy(l.done);
+    cudaFree(l.d_in); cudaFree(l.d_pre); cudaFree(l.d_out); cudaFree(l.d_spec1); cudaFree(l.d_spec2);
+    cudaFree(l.u8_in); cudaFree(l.u8_out); cudaFree(l.d_nyq);
+    l = Lane{};
+}
+size_t lane_bytes(const Geometry& g) {
+    return g.input_bytes() + g.pre_elems * g.elem_bytes() + g.output_bytes() + (g.spec_in_elems() + g.spec_out_elems()) * g.cplx_bytes();
+}
+// allocates every resource of one extra lane; on failure whatever was created is released again
+int make_lane(b2r_plan* p, Lane* out) {
     const Geometry& g = p->g;
-    const size_t eb = g.elem_bytes();
-    while (p->num_lanes() < lanes) {
-        Lane l;
+    const size_t eb = g.elem_bytes(), cb = g.cplx_bytes();
+    Lane l;
+    auto body = [&]() -> int {
         CU(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&l.done, cudaEventDisableTiming));
         CU(cudaMalloc(&l.d_in, g.input_bytes()));
         CU(cudaMalloc(&l.d_pre, g.pre_elems * eb));
         CU(cudaMalloc(&l.d_out, g.output_bytes()));
-        const size_t cb = g.cplx_bytes();
         CU(cudaMalloc((void**)&l.d_spec1, g.spec_in_elems() * cb));
         CU(cudaMalloc((void**)&l.d_spec2, g.spec_out_elems() * cb));
         CU(cudaMemset(l.d_in, 0, g.input_bytes()));
@@ -674,10 +704,41 @@ int b2r_plan_set_lanes(b2r_plan* p, uint32_t lanes) {
             CU(cudaMalloc((void**)&l.d_nyq, 3 * (size_t)g.spec_stride * cb));
             CU(cudaMemset(l.d_nyq, 0, 3 * (size_t)g.spec_stride * cb));
         }
-        p->device_bytes += g.input_bytes() + g.pre_elems * eb + g.output_bytes() +
-                           (g.spec_in_elems() + g.spec_out_elems()) * cb;
+        return B2R_SUCCESS;
+    };
+    const int rc = body();
+    if (rc) { free_lane(l); return rc; }
+    *out = l;
+    return B2R_SUCCESS;
+}
+}  // namespace
+
+int b2r_plan_set_lanes(b2r_plan* p, uint32_t lanes) {
+    if (!p || lanes < 1 || lanes > 8) return fail(B2R_ERR_INVALID_ARG, "lanes must be in [1, 8]");
+    DeviceGuard guard(p->device);
+    if (!guard.ok()) return fail(B2R_ERR_CUDA, "cudaSetDevice(%d) failed", p->device);
+    int rc = b2r_synchronize(p);   // nothing may be in flight while lanes come and go
+    if (rc) return rc;
+    while (p->num_lanes() < lanes) {
+        Lane l;
+        if ((rc = make_lane(p, &l))) return rc;
+        p->device_bytes += lane_bytes(p->g);
         p->extra.push_back(l);
     }
+    while (p->num_lanes() > lanes) {   // shrink: release the highest lanes and their staging buffers
+        Lane& l = p->extra.back();
+        if (l.u8_in) p->device_bytes -= b2r_plan_input_u8_bytes(p) + b2r_plan_output_u8_bytes(p);
+        free_lane(l);
+        p->device_bytes -= lane_bytes(p->g);
+        p->extra.pop_back();
+    }
+    {
+        std::lock_guard<std::mutex> g(p->tick_mu);   // tickets refer to lanes: start afresh
+        for (auto& ring : p->tick_ev) for (auto e : ring) if (e) cudaEventDestroy(e);
+        p->tick_ev.clear(); p->tick_pos.clear();
+        for (auto& e : p->tick_log) e = b2r_plan::TickEntry{};
+    }
+    p->next_lane = 0;
     CU(cudaDeviceSynchronize());
     return B2R_SUCCESS;
 }
@@ -705,7 +766,7 @@ int stamp_ticket(b2r_plan* p, uint32_t li, cudaStream_t s) {
 
 int b2r_enqueue_device(b2r_plan* p, const void* d_in, void* d_out) {
     if (!p || !d_in || !d_out) return fail(B2R_ERR_INVALID_ARG, "null argument");
-    CU(cudaSetDevice(p->device));
+    ON_PLAN_DEVICE(p);
     const uint32_t li = p->next_lane++ % p->num_lanes();
     const Lane l = p->lane(li);
     int rc = launch_frame(p, l.stream, d_in, d_out, nullptr, li ? &l : nullptr);
@@ -716,7 +777,7 @@ int b2r_enqueue_device(b2r_plan* p, const void* d_in, void* d_out) {
 
 int b2r_enqueue_host(b2r_plan* p, const void* host_in, void* host_out) {
     if (!p || !host_in || !host_out) return fail(B2R_ERR_INVALID_ARG, "null argument");
-    CU(cudaSetDevice(p->device));
+    ON_PLAN_DEVICE(p);
     const uint32_t li = p->next_lane++ % p->num_lanes();
     const Lane l = p->lane(li);
     CU(cudaMemcpyAsync(l.d_in, host_in, p->g.input_bytes(), cudaMemcpyHostToDevice, l.stream));
@@ -734,9 +795,12 @@ namespace {
 int u8_buffers(b2r_plan* p, uint32_t li, unsigned char** in, unsigned char** out) {
     unsigned char** pin = li ? &p->extra[li - 1].u8_in : &p->u8_in0;
     unsigned char** pout = li ? &p->extra[li - 1].u8_out : &p->u8_out0;
-    if (!*pin) {
-        CU(cudaMalloc((void**)pin, b2r_plan_input_u8_bytes(p)));
-        CU(cudaMalloc((void**)pout, b2r_plan_output_u8_bytes(p)));
+    if (!*pin) {   // both buffers exist before either pointer is published
+        unsigned char *a = nullptr, *b = nullptr;
+        CU(cudaMalloc((void**)&a, b2r_plan_input_u8_bytes(p)));
+        cudaError_t e2 = cudaMalloc((void**)&b, b2r_plan_output_u8_bytes(p));
+        if (e2 != cudaSuccess) { cudaFree(a); return fail(B2R_ERR_CUDA, "cudaMalloc failed: %s", cudaGetErrorString(e2)); }
+        *pin = a; *pout = b;
         p->device_bytes += b2r_plan_input_u8_bytes(p) + b2r_plan_output_u8_bytes(p);
     }
     *in = *pin; *out = *pout;
@@ -746,7 +810,7 @@ int u8_buffers(b2r_plan* p, uint32_t li, unsigned char** in, unsigned char** out
 
 int b2r_upload_u8(b2r_plan* p, const unsigned char* host_hwc) {
     if (!p || !host_hwc) return fail(B2R_ERR_INVALID_ARG, "null argument");
-    CU(cudaSetDevice(p->device));
+    ON_PLAN_DEVICE(p);
     unsigned char *in, *out;
     int rc = u8_buffers(p, 0, &in, &out);
     if (rc) return rc;
@@ -760,7 +824,7 @@ int b2r_upload_u8(b2r_plan* p, const unsigned char* host_hwc) {
 
 int b2r_download_u8(b2r_plan* p, unsigned char* host_hwc) {
     if (!p || !host_hwc) return fail(B2R_ERR_INVALID_ARG, "null argument");
-    CU(cudaSetDevice(p->device));
+    ON_PLAN_DEVICE(p);
     unsigned char *in, *out;
     int rc = u8_buffers(p, 0, &in, &out);
     if (rc) return rc;
@@ -774,7 +838,7 @@ int b2r_download_u8(b2r_plan* p, unsigned char* host_hwc) {
 
 int b2r_enqueue_host_u8(b2r_plan* p, const unsigned char* host_in, unsigned char* host_out) {
     if (!p || !host_in || !host_out) return fail(B2R_ERR_INVALID_ARG, "null argument");
-    CU(cudaSetDevice(p->device));
+    ON_PLAN_DEVICE(p);
     const uint32_t li = p->next_lane++ % p->num_lanes();
     const Lane l = p->lane(li);
     unsigned char *in, *out;
@@ -818,7 +882,7 @@ void b2r_host_free(void* ptr) { if (ptr) cudaFreeHost(ptr); }
 
 int b2r_timer_start(b2r_plan* p) {
     if (!p) return fail(B2R_ERR_INVALID_ARG, "null plan");
-    CU(cudaSetDevice(p->device));
+    ON_PLAN_DEVICE(p);
     CU(cudaEventRecord(p->ev0, p->stream));
     for (Lane& l : p->extra) CU(cudaStreamWaitEvent(l.stream, p->ev0, 0));   // every lane starts after t0
     return B2R_SUCCESS;
@@ -826,7 +890,7 @@ int b2r_timer_start(b2r_plan* p) {
 
 int b2r_timer_stop(b2r_plan* p, double* ms) {
     if (!p) return fail(B2R_ERR_INVALID_ARG, "null plan");
-    CU(cudaSetDevice(p->device));
+    ON_PLAN_DEVICE(p);
     for (Lane& l : p->extra) {                                                // t1 is after every lane's tail
         CU(cudaEventRecord(l.done, l.stream));
         CU(cudaStreamWaitEvent(p->stream, l.done, 0));
@@ -842,8 +906,13 @@ int b2r_timer_stop(b2r_plan* p, double* ms) {
 
 int b2r_profile_kernels(b2r_plan* p, uint32_t num_iter, double* ms_per_kernel) {
     if (!p || !num_iter || !ms_per_kernel) return fail(B2R_ERR_INVALID_ARG, "null argument");
-    CU(cudaSetDevice(p->device));
-    std::vector<cudaEvent_t> ev(5 * (size_t)num_iter);
+    ON_PLAN_DEVICE(p);
+    struct Events {   // destroyed on every return path
+        std::vector<cudaEvent_t> v;
+        ~Events() { for (auto e : v) if (e) cudaEventDestroy(e); }
+    } evs;
+    evs.v.assign(5 * (size_t)num_iter, nullptr);
+    std::vector<cudaEvent_t>& ev = evs.v;
     for (auto& e : ev) CU(cudaEventCreate(&e));
     for (uint32_t i = 0; i < num_iter; ++i) {
         int rc = launch_frame(p, p->stream, nullptr, nullptr, &ev[5 * (size_t)i]);
@@ -858,13 +927,12 @@ int b2r_profile_kernels(b2r_plan* p, uint32_t num_iter, double* ms_per_kernel) {
             CU(cudaEventElapsedTime(&t, ev[5 * (size_t)i + k], ev[5 * (size_t)i + k + 1]));
             ms_per_kernel[k] += (double)t / num_iter;
         }
-    for (auto& e : ev) cudaEventDestroy(e);
     return B2R_SUCCESS;
 }
 
 int b2r_synchronize(b2r_plan* p) {
     if (!p) return fail(B2R_ERR_INVALID_ARG, "null plan");
-    CU(cudaSetDevice(p->device));
+    ON_PLAN_DEVICE(p);
     for (Lane& l : p->extra) CU(cudaStreamSynchronize(l.stream));
     CU(cudaStreamSynchronize(p->stream));
     return B2R_SUCCESS;

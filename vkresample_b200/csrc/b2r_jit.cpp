@@ -126,18 +126,36 @@ std::string slurp(const std::string& path) {
     ss << f.rdbuf();
     return ss.str();
 }
+// The cubin cache holds GPU code that is loaded without further checks, so it must live in a directory only
+// this user can write: B2R_CACHE_DIR or $HOME/.cache/b2resample, created 0700 and verified (owner == us, no
+// group / other write bit).  No private directory (HOME unset, wrong owner, ...) -> "" = caching disabled;
+// there is no fallback to a shared location such as /tmp.
 std::string cache_dir() {
-    if (const char* e = getenv("B2R_CACHE_DIR")) return e;
-    const char* home = getenv("HOME");
-    return std::string(home ? home : "/tmp") + "/.cache/b2resample";
+    std::string d;
+    if (const char* e = getenv("B2R_CACHE_DIR")) d = e;
+    else if (const char* home = getenv("HOME")) { if (*home) d = std::string(home) + "/.cache/b2resample"; }
+    if (d.empty()) return d;
+    for (size_t i = 1; i <= d.size(); ++i)
+        if (i == d.size() || d[i] == '/') mkdir(d.substr(0, i).c_str(), 0700);
+    struct stat st;
+    if (stat(d.c_str(), &st) != 0 || !S_ISDIR(st.st_mode) || st.st_uid != geteuid() || (st.st_mode & (S_IWGRP | S_IWOTH))) return "";
+    return d;
 }
-void mkdirs(const std::string& p) {
-    for (size_t i = 1; i <= p.size(); ++i)
-        if (i == p.size() || p[i] == '/') mkdir(p.substr(0, i).c_str(), 0755);
+// write `data` to `path` through a private temporary name; false (and nothing published) on any I/O error
+bool publish(const std::string& path, const std::string& data, const std::string& tag) {
+    const std::string tmp = path + tag;
+    {
+        std::ofstream f(tmp, std::ios::binary);
+        f.write(data.data(), (std::streamsize)data.size());
+        f.flush();
+        if (!f.good()) { f.close(); remove(tmp.c_str()); return false; }
+    }
+    if (rename(tmp.c_str(), path.c_str()) != 0) { remove(tmp.c_str()); return false; }
+    return true;
 }
 
 // per-plan state: one module with the kernels this plan needs
-struct RowCtx { JitModule* m; CUfunction fn = nullptr, fn_c2c = nullptr; int threads = 0, ppb = 1; bool bulk = false; int sms = 0; bool dbl = false; };
+struct RowCtx { JitModule* m; CUfunction fn = nullptr, fn_c2c = nullptr; int threads = 0, ppb = 1, ppb_c2c = 1; bool bulk = false; int sms = 0; bool dbl = false; };
 struct ColCtx { JitModule* m; CUfunction fn = nullptr; int threads = 0, cc = 4; bool dbl = false; };
 
 }  // namespace
@@ -212,7 +230,7 @@ cudaError_t run_c2c(cudaStream_t s, const C2rArgs& a, int, size_t smem, const vo
     float scale = a.scale;
     double scale_d = 1.0 / (double)a.dm.up_w;
     void* args[] = {(void*)&a.spec, (void*)&a.nyq, (void*)&a.pre, (void*)&a.tw, &plan, (void*)&a.dm, &rows, k->dbl ? (void*)&scale_d : (void*)&scale};
-    return cu2rt(api().cuLaunchKernel(k->fn_c2c, (rows + k->ppb - 1) / k->ppb, 1, 1, k->threads, k->ppb, 1, (unsigned)smem,
+    return cu2rt(api().cuLaunchKernel(k->fn_c2c, (rows + k->ppb_c2c - 1) / k->ppb_c2c, 1, 1, k->threads, k->ppb_c2c, 1, (unsigned)smem,
                                       (CUstream)s, args, nullptr));
 }
 cudaError_t run_cols(cudaStream_t s, const ColsArgs& a, int, size_t smem, const void* ctx) {
@@ -251,9 +269,14 @@ bool jit_build(const JitRequest& rq, JitModule** out_mod, RowImpl* r2c, ColImpl*
         n << "b2r::k_cols<" << type_of(rq.h) << ", " << type_of(rq.uh) << ", " << rq.cc << ">";
         names.push_back(n.str());
     }
+    // the bulk-copy C2R kernel adds 4*nx staging elements to the workspace; when that does not fit one CTA
+    // (e.g. fp64 3840 -> 7680) the direct-load kernel, whose footprint is the workspace alone, is compiled instead
+    const size_t c2r_bulk_bytes = 16 + 4 * (size_t)c2r_stage_row_elems(rq.nx) * cb + (size_t)smem_padded_len(rq.uw.n) * cb;
+    const bool c2r_bulk = c2r_bulk_bytes <= 227u * 1024u;
     if (rq.want_c2r) {
         std::ostringstream n;
-        n << "b2r::k_c2r_rows_bulk<" << type_of(rq.uw) << ", " << tin << ", " << (rq.up2 ? "true" : "false") << ">";
+        if (c2r_bulk) n << "b2r::k_c2r_rows_bulk<" << type_of(rq.uw) << ", " << tin << ", " << (rq.up2 ? "true" : "false") << ">";
+        else n << "b2r::k_c2r_rows<" << type_of(rq.uw) << ", " << tin << ", 1, " << (rq.up2 ? "true" : "false") << ">";
         names.push_back(n.str());
         if (rq.c2c) {
             std::ostringstream m;
@@ -279,66 +302,76 @@ bool jit_build(const JitRequest& rq, JitModule** out_mod, RowImpl* r2c, ColImpl*
     const uint64_t key = fnv(hdr, fnv(source + std::to_string(vmaj * 100 + vmin)));
     char keyhex[32];
     snprintf(keyhex, sizeof keyhex, "%016llx", (unsigned long long)key);
-    const std::string cpath = cache_dir() + "/" + keyhex + ".cubin", npath = cache_dir() + "/" + keyhex + ".names";
+    const std::string cdir = cache_dir();   // "" = no private cache directory: compile every time
+    const std::string cpath = cdir + "/" + keyhex + ".cubin", npath = cdir + "/" + keyhex + ".names";
 
-    std::string cubin = slurp(cpath);
+    std::string cubin;
     std::vector<std::string> lowered;
-    if (!cubin.empty()) {
-        std::istringstream nf(slurp(npath));
-        std::string line;
-        while (std::getline(nf, line)) if (!line.empty()) lowered.push_back(line);
-        if (lowered.size() != names.size()) { cubin.clear(); lowered.clear(); }
-    }
-    if (cubin.empty()) {
-        if (rq.cache_only) { *err = "no cached JIT build for this size"; return false; }
-        nvrtcProgram prog = nullptr;
-        if (a.nvrtcCreateProgram(&prog, source.c_str(), "b2r_jit.cu", 0, nullptr, nullptr) != 0) { *err = "nvrtcCreateProgram failed"; return false; }
-        for (const auto& n : names) a.nvrtcAddNameExpression(prog, n.c_str());
-        const std::string inc1 = "-I" + csrc;
-        std::string cuda_inc = "-I/usr/local/cuda/include";
-        if (const char* e = getenv("CUDA_HOME")) cuda_inc = std::string("-I") + e + "/include";
-        const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", inc1.c_str(), cuda_inc.c_str(), "-default-device",
-                              "-lineinfo", "-diag-suppress=550"};
-        const int rc = a.nvrtcCompileProgram(prog, 7, opts);
-        if (rc != 0) {
-            size_t ls = 0;
-            a.nvrtcGetProgramLogSize(prog, &ls);
-            std::string log(ls, 0);
-            if (ls) a.nvrtcGetProgramLog(prog, &log[0]);
-            *err = "NVRTC compilation failed: " + log.substr(0, 400);
+    JitModule* m = nullptr;
+    // attempt 0 may use a cached cubin; if the driver rejects it (truncated / foreign file) the entry is deleted
+    // and attempt 1 compiles afresh
+    for (int attempt = 0; attempt < 2 && !m; ++attempt) {
+        bool from_cache = false;
+        cubin.clear(); lowered.clear();
+        if (attempt == 0 && !cdir.empty()) {
+            cubin = slurp(cpath);
+            if (!cubin.empty()) {
+                std::istringstream nf(slurp(npath));
+                std::string line;
+                while (std::getline(nf, line)) if (!line.empty()) lowered.push_back(line);
+                if (lowered.size() != names.size()) { cubin.clear(); lowered.clear(); }
+                else from_cache = true;
+            }
+        }
+        if (cubin.empty()) {
+            if (rq.cache_only) { *err = "no cached JIT build for this size"; return false; }
+            nvrtcProgram prog = nullptr;
+            if (a.nvrtcCreateProgram(&prog, source.c_str(), "b2r_jit.cu", 0, nullptr, nullptr) != 0) { *err = "nvrtcCreateProgram failed"; return false; }
+            for (const auto& n : names) a.nvrtcAddNameExpression(prog, n.c_str());
+            const std::string inc1 = "-I" + csrc;
+            std::string cuda_inc = "-I/usr/local/cuda/include";
+            if (const char* e = getenv("CUDA_HOME")) cuda_inc = std::string("-I") + e + "/include";
+            const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", inc1.c_str(), cuda_inc.c_str(), "-default-device",
+                                  "-lineinfo", "-diag-suppress=550"};
+            const int rc = a.nvrtcCompileProgram(prog, 7, opts);
+            if (rc != 0) {
+                size_t ls = 0;
+                a.nvrtcGetProgramLogSize(prog, &ls);
+                std::string log(ls, 0);
+                if (ls) a.nvrtcGetProgramLog(prog, &log[0]);
+                *err = "NVRTC compilation failed: " + log.substr(0, 400);
+                a.nvrtcDestroyProgram(&prog);
+                return false;
+            }
+            for (const auto& n : names) {
+                const char* ln = nullptr;
+                a.nvrtcGetLoweredName(prog, n.c_str(), &ln);
+                lowered.push_back(ln ? ln : "");
+            }
+            size_t cs = 0;
+            a.nvrtcGetCUBINSize(prog, &cs);
+            cubin.resize(cs);
+            a.nvrtcGetCUBIN(prog, &cubin[0]);
             a.nvrtcDestroyProgram(&prog);
+            // publish atomically (several worker threads / processes may build the same key at once): private
+            // names first, stream state checked, then rename; the .names file goes last and gates the cache hit
+            if (!cdir.empty()) {
+                const std::string tag = "." + std::to_string((long long)getpid()) + "." + std::to_string((unsigned long long)(uintptr_t)&cubin);
+                std::string nm;
+                for (const auto& l : lowered) nm += l + "\n";
+                if (publish(cpath, cubin, tag)) { if (!publish(npath, nm, tag)) remove(cpath.c_str()); }
+            }
+        }
+        m = new JitModule();
+        if (a.cuModuleLoadData(&m->mod, cubin.data()) != 0) {
+            delete m;
+            m = nullptr;
+            if (from_cache) { remove(npath.c_str()); remove(cpath.c_str()); continue; }   // bad cache entry: drop it, recompile once
+            *err = "cuModuleLoadData failed";
             return false;
         }
-        for (const auto& n : names) {
-            const char* ln = nullptr;
-            a.nvrtcGetLoweredName(prog, n.c_str(), &ln);
-            lowered.push_back(ln ? ln : "");
-        }
-        size_t cs = 0;
-        a.nvrtcGetCUBINSize(prog, &cs);
-        cubin.resize(cs);
-        a.nvrtcGetCUBIN(prog, &cubin[0]);
-        a.nvrtcDestroyProgram(&prog);
-        // publish atomically (several worker threads / processes may build the same key at once):
-        // write to a private name, then rename; the .names file goes last and gates the cache hit
-        mkdirs(cache_dir());
-        const std::string tag = "." + std::to_string((long long)getpid()) + "." + std::to_string((unsigned long long)(uintptr_t)&cubin);
-        {
-            std::ofstream cf(cpath + tag, std::ios::binary);
-            cf.write(cubin.data(), (std::streamsize)cubin.size());
-        }
-        {
-            std::ofstream nf(npath + tag);
-            for (const auto& l : lowered) nf << l << "\n";
-        }
-        if (rename((cpath + tag).c_str(), cpath.c_str()) != 0 || rename((npath + tag).c_str(), npath.c_str()) != 0) {
-            remove((cpath + tag).c_str());
-            remove((npath + tag).c_str());
-        }
     }
-
-    JitModule* m = new JitModule();
-    if (a.cuModuleLoadData(&m->mod, cubin.data()) != 0) { *err = "cuModuleLoadData failed"; delete m; return false; }
+    if (!m) { *err = "cuModuleLoadData failed"; return false; }
     size_t idx = 0;
     auto get = [&](CUfunction* f) { return a.cuModuleGetFunction(f, m->mod, lowered[idx++].c_str()) == 0; };
     int dev = 0, sms = 0;
@@ -370,13 +403,13 @@ bool jit_build(const JitRequest& rq, JitModule** out_mod, RowImpl* r2c, ColImpl*
         cols->ctx = &m->cols; cols->prepare = &prep_col; cols->launch = &run_cols;
     }
     if (rq.want_c2r) {
-        m->c2r.m = m; m->c2r.threads = rq.uw.threads; m->c2r.ppb = ppb_uw; m->c2r.bulk = true; m->c2r.sms = sms; m->c2r.dbl = dbl;
+        m->c2r.m = m; m->c2r.threads = rq.uw.threads; m->c2r.ppb = c2r_bulk ? ppb_uw : 1; m->c2r.ppb_c2c = ppb_uw; m->c2r.bulk = c2r_bulk; m->c2r.sms = sms; m->c2r.dbl = dbl;
         ok = ok && get(&m->c2r.fn);
         report(names[idx - 1].c_str(), m->c2r.fn);
         if (rq.c2c) ok = ok && get(&m->c2r.fn_c2c);
         *c2r = RowImpl{};
-        c2r->name = "c2r_rows_bulk<jit>"; c2r->is_static = true; c2r->is_jit = true; c2r->sched = rq.uw; c2r->ppb = 1;
-        c2r->smem = 16 + 4 * (size_t)c2r_stage_row_elems(rq.nx) * cb + (size_t)smem_padded_len(rq.uw.n) * cb;
+        c2r->name = c2r_bulk ? "c2r_rows_bulk<jit>" : "c2r_rows<jit>"; c2r->is_static = true; c2r->is_jit = true; c2r->sched = rq.uw; c2r->ppb = 1;
+        c2r->smem = c2r_bulk ? c2r_bulk_bytes : (size_t)smem_padded_len(rq.uw.n) * cb;
         c2r->ctx = &m->c2r; c2r->prepare = &prep_row; c2r->c2r = &run_c2r;
         c2r->c2c = &run_c2c; c2r->prepare_c2c = &prep_row_c2c; c2r->ppb_c2c = ppb_uw;
         c2r->smem_c2c = (size_t)ppb_uw * smem_padded_len(rq.uw.n) * cb;

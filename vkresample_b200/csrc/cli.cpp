@@ -373,6 +373,9 @@ struct Pipeline {
     uint32_t next_decode = 0, next_submit = 0, next_encode = 0, written = 0;
     int error = 0;
     double t_decode = 0, t_encode = 0, t_wait = 0;    // summed over workers (seconds)
+    std::chrono::steady_clock::time_point t_start = std::chrono::steady_clock::now();
+    double at_ring = 0, at_plan = 0, at_first = 0, at_last = 0;   // seconds since t_start: ring allocated, plan ready, first / last file written
+    double since_start() const { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count(); }
 
     uint32_t file_of(uint32_t k) const { return first + k * stride; }
 
@@ -427,6 +430,8 @@ struct Pipeline {
                 t_encode += std::chrono::duration<double>(t2 - t1).count();
                 s.state = FREE;
                 ++written;
+                at_last = since_start();
+                if (written == 1) at_first = at_last;
                 cv.notify_all();
             } else {
                 auto t0 = clk::now();
@@ -459,6 +464,7 @@ struct Pipeline {
             printf("VRAM per GPU: %d MB (%u lanes), %u codec threads + 1 submit thread per GPU\n", (int)(pi.device_bytes >> 20), lanes, cfg.num_threads);
         std::lock_guard<std::mutex> g(mu);
         info = pi;
+        at_plan = since_start();
         return 0;
     }
 
@@ -480,6 +486,7 @@ struct Pipeline {
             s.out = (unsigned char*)b2r_host_alloc((size_t)3 * info.up_w * info.up_h);
             if (!s.in || !s.out) { printf("pinned allocation failed: %s\n", b2r_last_error()); return -4; }
         }
+        at_ring = since_start();
         std::vector<std::thread> th;
         th.emplace_back([this] { int rc = create_plan(); if (rc) fail_with(rc); else submit_loop(); });
         for (uint32_t t = 0; t < cfg.num_threads; ++t) th.emplace_back([this] { worker_loop(); });
@@ -490,6 +497,10 @@ struct Pipeline {
         b2r_device_name(device, dev_name, sizeof dev_name);
         printf("GPU %d finished: %u frames, codec thread-seconds: decode %.2f, encode %.2f, waiting for the GPU %.2f. Device name: %s API:%s\n",
                gpu_index, written, t_decode, t_encode, t_wait, dev_name, b2r_version());
+        printf("GPU %d timeline: pinned ring ready at %.2f s, plan ready at %.2f s, first file written at %.2f s, last at %.2f s",
+               gpu_index, at_ring, at_plan, at_first, at_last);
+        if (written > 1 && at_last > at_first) printf(" -> steady state %.1f frames/s", (written - 1) / (at_last - at_first));
+        printf("\n");
         if (plan) b2r_plan_destroy(plan);
         return error;
     }
