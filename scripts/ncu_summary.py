@@ -24,8 +24,8 @@ WANT = [
     ("lts__t_sector_hit_rate.pct", "L2 hit %"),
     ("l1tex__t_sector_hit_rate.pct", "L1 hit %"),
 ]
-SHORT = {"k_r2c_rows": "r2c_rows", "k_cols": "cols", "k_c2r_rows": "c2r_rows", "k_sharpen": "sharpen",
-         "k_c2r_sharpen": "c2r_sharpen"}
+SHORT = {"k_r2c_rows": "r2c_rows", "k_cols": "cols", "k_c2r_sharpen": "c2r_sharpen", "k_c2r_rows": "c2r_rows",
+         "k_sharpen_fix": "sharpen_fix", "k_sharpen": "sharpen"}   # first match wins (dict order)
 
 
 def main():

@@ -185,16 +185,22 @@ template <class P, int PPB> static void emu_c2r(FrameCtx& c, const P plan, const
 static int g_cols_grouped = 0;   // opt-in like the product (B2R_COLS_GROUPED=1)
 static int g_fused_nsp = 0;      // > 0: K7 + K8 through the fused strip kernel (b2r_fused.cuh) with this many strips per plane
 
-// fused C2R + sharpen + boundary fix-up, as launch_frame / run_fused do it (fp32, static schedules)
+// fused C2R + sharpen + boundary fix-up, as launch_frame / run_fused do it (fp32 / fp16, static schedules)
 template <class P> static void emu_fused(FrameCtx& c, const P plan, const HostFft& hf, void* out) {
+    const bool half = c.precision == 2;
     const int nsp = g_fused_nsp, ppp = c.g.up_h / 2;
     const float2* tw = hf.twiddles.data();
     const float scale = 1.0f / (float)c.g.up_w;
     const bool up2 = (c.g.up_w == 2 * c.g.w);
     Dim3 grid, block; block.x = P::kT; grid.x = 3 * nsp;
     b2r_emu::launch(grid, block, fused_smem_bytes(P::kN, c.g.nx), [&] {
-        if (up2) k_c2r_sharpen_f32<P, true>(c.spec2.data(), (float*)out, (float*)c.pre.data(), tw, plan, c.dm, scale, nsp);
-        else k_c2r_sharpen_f32<P, false>(c.spec2.data(), (float*)out, (float*)c.pre.data(), tw, plan, c.dm, scale, nsp);
+        if (half) {
+            if (up2) k_c2r_sharpen_f16<P, true>(c.spec2.data(), (__half*)out, (__half*)c.pre.data(), tw, plan, c.dm, scale, nsp);
+            else k_c2r_sharpen_f16<P, false>(c.spec2.data(), (__half*)out, (__half*)c.pre.data(), tw, plan, c.dm, scale, nsp);
+        } else {
+            if (up2) k_c2r_sharpen_f32<P, true>(c.spec2.data(), (float*)out, (float*)c.pre.data(), tw, plan, c.dm, scale, nsp);
+            else k_c2r_sharpen_f32<P, false>(c.spec2.data(), (float*)out, (float*)c.pre.data(), tw, plan, c.dm, scale, nsp);
+        }
     });
     std::vector<int> fix;
     for (int q = 1; q < nsp; ++q) {
@@ -202,8 +208,11 @@ template <class P> static void emu_fused(FrameCtx& c, const P plan, const HostFf
         fix.push_back((b - 2) | kFixCornerBit); fix.push_back(b - 1); fix.push_back(b);
     }
     fix.push_back((c.g.up_h - 2) | kFixCornerBit); fix.push_back(c.g.up_h - 1);
-    Dim3 g2, b2; b2.x = 32; g2.x = (c.g.up_w / 4 + 31) / 32; g2.y = (unsigned)fix.size(); g2.z = 3;
-    b2r_emu::launch(g2, b2, 0, [&] { k_sharpen_fix_f32<0>((const float*)c.pre.data(), (float*)out, c.dm, fix.data()); });
+    Dim3 g2, b2; b2.x = 32; g2.x = (c.g.up_w / (half ? 8 : 4) + 31) / 32; g2.y = (unsigned)fix.size(); g2.z = 3;
+    b2r_emu::launch(g2, b2, 0, [&] {
+        if (half) k_sharpen_fix_f16<0>((const __half*)c.pre.data(), (__half*)out, c.dm, fix.data());
+        else k_sharpen_fix_f32<0>((const float*)c.pre.data(), (float*)out, c.dm, fix.data());
+    });
 }
 
 template <class PF, class PI, int CC>
@@ -375,7 +384,7 @@ int b2r_emu_frame(int w, int h, float upscale, int precision, float sharpen_cons
         }
     }
     bool fused_done = false;
-    if (g_fused_nsp > 0 && precision == 0 && use_static && !g_c2c) {   // K7 + K8 fused
+    if (g_fused_nsp > 0 && (precision == 0 || precision == 2) && use_static && !g_c2c) {   // K7 + K8 fused
 #define X(N, PPB, T, ...) \
         if (!fused_done && g.up_w == N) { using P = StaticFft<N, T, __VA_ARGS__>; host_fft_of<P>(&hf); emu_fused<P>(c, P{}, hf, out); fused_done = true; used |= 4; }
         B2R_STATIC_C2R_ROWS(X)

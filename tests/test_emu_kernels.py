@@ -317,9 +317,10 @@ def test_random_geometries():
         done += 1
 
 
-@pytest.mark.parametrize("w,h,up,nsp", [(256, 128, 2.0, 1), (256, 128, 2.0, 5), (256, 128, 2.0, 42), (128, 64, 2.0, 3),
-                                        (512, 36, 1.0, 4), (256, 24, 2.0, 8)])
-def test_fused_c2r_sharpen_equals_separate_kernels(w, h, up, nsp):
+@pytest.mark.parametrize("w,h,up,nsp,prec", [(256, 128, 2.0, 1, 0), (256, 128, 2.0, 5, 0), (256, 128, 2.0, 42, 0), (128, 64, 2.0, 3, 0),
+                                             (512, 36, 1.0, 4, 0), (256, 24, 2.0, 8, 0),
+                                             (256, 128, 2.0, 5, 2), (256, 48, 2.0, 16, 2), (512, 36, 1.0, 4, 2), (128, 64, 2.0, 1, 2)])
+def test_fused_c2r_sharpen_equals_separate_kernels(w, h, up, nsp, prec):
     """K7 + K8 as ONE kernel (b2r_fused.cuh: strip CTAs, rows kept in shared memory, boundary rows through the
     pre-sharpen buffer + k_sharpen_fix) against the separate C2R + tolerance-bound sharpen kernels: the same
     bytes, for one strip per plane, many strips, the smallest strips (3 pairs), up == 1 (no x zero padding:
@@ -330,19 +331,23 @@ def test_fused_c2r_sharpen_equals_separate_kernels(w, h, up, nsp):
     L.b2r_emu_set_sharpen_fast(1)
     try:
         L.b2r_emu_set_fused(0)
-        sep = eu.frame(x, up, 0, 0.2, plan)
+        sep = eu.frame(x, up, prec, 0.2, plan)
         L.b2r_emu_set_fused(nsp)
-        fus = eu.frame(x, up, 0, 0.2, plan)
+        fus = eu.frame(x, up, prec, 0.2, plan)
     finally:
         L.b2r_emu_set_fused(0)
         L.b2r_emu_set_sharpen_fast(0)
     assert sep["used_static"] & 4 and fus["used_static"] & 4
-    assert np.isfinite(fus["out"]).all()
-    bad = np.argwhere(sep["out"].view(np.uint32) != fus["out"].view(np.uint32))
+    assert np.isfinite(fus["out"].astype(np.float64)).all()
+    bits = np.uint16 if prec == 2 else np.uint32
+    bad = np.argwhere(sep["out"].view(bits) != fus["out"].view(bits))
     assert bad.size == 0, (len(bad), bad[:10])
     # and the separate default path itself is within tolerance of the oracle
-    ref = vo.sharpen(sep["pre"], plan, 0.2, 0)
-    assert np.abs(sep["out"].astype(np.float64) - ref.astype(np.float64)).max() <= 1e-5
+    ref = vo.sharpen(sep["pre"], plan, 0.2, prec)
+    ok = np.ones(ref.shape, bool)
+    if prec == 2:
+        ok[:, -1, :] = False   # fp16: the reference's last row depends on stale memory
+    assert np.abs(sep["out"].astype(np.float64) - ref.astype(np.float64))[ok].max() <= (1e-2 if prec == 2 else 1e-5)
 
 
 @pytest.mark.parametrize("w,h,prec", [(256, 16, 0), (512, 12, 2), (640, 8, 0)])

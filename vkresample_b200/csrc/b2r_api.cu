@@ -47,13 +47,15 @@ int fail(int code, const char* fmt, ...) {
 
 // Entry points run on the plan's device and leave the caller's current device as they found it.
 struct DeviceGuard {
-    int prev = -1;
+    int prev = -1, dev_ = -1;
     bool good = true;
-    explicit DeviceGuard(int dev) {
+    explicit DeviceGuard(int dev) : dev_(dev) {
         if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-        if (prev != dev) good = cudaSetDevice(dev) == cudaSuccess;
+        // always: cudaSetDevice is also what creates the primary context and makes it current on this thread,
+        // which the driver-API calls of the plan-time JIT (cuModuleLoadData, ...) rely on
+        good = cudaSetDevice(dev) == cudaSuccess;
     }
-    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+    ~DeviceGuard() { if (prev >= 0 && prev != dev_) cudaSetDevice(prev); }
     bool ok() const { return good; }
 };
 #define ON_PLAN_DEVICE(p)                                                                           \
@@ -385,7 +387,7 @@ int build(b2r_plan* p) {
         sa.exact = (p->flags & B2R_FLAG_EXACT_SHARPEN) != 0;
         const int ppp = g.up_h / 2;
         const bool want = !(p->flags & B2R_FLAG_SEPARATE_SHARPEN) && env_int("B2R_FUSED", 1) != 0;
-        bool ok = want && !p->c2c && g.precision == 0 && sharpen_fast_applies(sa) && p->k_c2r.fused && !p->k_c2r.is_jit &&
+        bool ok = want && !p->c2c && (g.precision == 0 || g.precision == 2) && sharpen_fast_applies(sa) && p->k_c2r.fused && !p->k_c2r.is_jit &&
                   ppp >= 6 && fused_smem_bytes(g.up_w, g.nx) <= smem_max;
         if (ok && p->k_c2r.prepare_fused(g.precision, g.nx) != cudaSuccess) { (void)cudaGetLastError(); ok = false; }
         if (ok) {

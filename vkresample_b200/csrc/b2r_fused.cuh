@@ -262,6 +262,227 @@ B2R_KERNEL k_sharpen_fix_f32(const float* __restrict__ pre, float* __restrict__ 
     sharpen_fix_f32_impl(pre, out, dm, list);
 }
 
+
+// ---- fp16 storage (precision 2) ---------------------------------------------------------------------
+// Same strip structure; the rows are kept as HALF clamped magnitudes (the reference's sharpen shader computes
+// in float16_t on the half C2R output, VkResample.cpp:823-827, vkFFT.h:3525-3527), eight pixels per group and
+// two pixels per instruction (cas_row_f16).  t = min(|up2_h * half(v)|, 1) with individually rounded half
+// operations, i.e. exactly what k_sharpen_fast_f16 derives from the stored plane.
+#if defined(__CUDA_ARCH__)
+B2R_DEV __half fused_tap_h(__half up2, __half v) { return __hmin(__habs(__hmul(up2, v)), __float2half_rn(1.0f)); }
+#else
+B2R_DEV __half fused_tap_h(__half up2, __half v) {
+    const __half2 r = cas_tap2(__halves2half2(up2, up2), __halves2half2(v, v));
+    return __low2half(r);
+}
+#endif
+
+B2R_DEV __half2 fused_u2h(unsigned w) { __half2 h; *reinterpret_cast<unsigned*>(&h) = w; return h; }
+B2R_DEV unsigned fused_h2u(__half2 h) { return *reinterpret_cast<unsigned*>(&h); }
+
+// the thread's eight own values `v` of one row + halo columns -> CasRowH<8>
+template <bool SHFL>
+B2R_DEV void fused_taps8h(const __half* row, const uint4 v, int x0, int n, __half right_end, CasRowH<8>& t) {
+    t.b[0] = fused_u2h(v.x); t.b[1] = fused_u2h(v.y); t.b[2] = fused_u2h(v.z); t.b[3] = fused_u2h(v.w);
+    __half l, r;
+#if !defined(B2R_HOST_EMU)
+    if constexpr (SHFL) {
+        const int lane = (int)B2R_TID_X & 31;
+        l = __high2half(fused_u2h(__shfl_up_sync(0xffffffffu, v.w, 1)));
+        r = __low2half(fused_u2h(__shfl_down_sync(0xffffffffu, v.x, 1)));
+        if (lane == 0) l = row[x0 > 0 ? x0 - 1 : 0];
+        if (lane == 31) r = row[x0 + 8 < n ? x0 + 8 : x0];
+        if (x0 + 8 >= n) r = right_end;
+        t.link(l, r);
+        return;
+    }
+#endif
+    l = row[x0 > 0 ? x0 - 1 : 0];
+    r = (x0 + 8 < n) ? row[x0 + 8] : right_end;
+    t.link(l, r);
+}
+
+template <class P, bool UP2>
+B2R_KERNEL B2R_LAUNCH_BOUNDS((P::kT), (fused_min_blocks<P>()))
+k_c2r_sharpen_f16(const real2* __restrict__ spec, __half* __restrict__ out, __half* __restrict__ pre,
+                  const real2* __restrict__ tw, const P plan, const FrameDims dm, const real scale, const int nsp) {
+    constexpr int NP = 8;
+    const int T = plan.threads(), tid = (int)B2R_TID_X, n = plan.n();
+    const int ppp = dm.up_h >> 1;
+    const int c = (int)B2R_BID_X / nsp, q = (int)B2R_BID_X - c * nsp;
+    const int j0 = fused_strip_begin(q, nsp, ppp), j1 = fused_strip_begin(q + 1, nsp, ppp);
+    const int S = j1 - j0;
+    const bool top = (j0 == 0);
+    const int row_elems = c2r_stage_row_elems(dm.nx);
+    unsigned char* const smem_base = B2R_SMEM(unsigned char);
+    unsigned long long* const bar = reinterpret_cast<unsigned long long*>(smem_base);
+    real2* const stg = reinterpret_cast<real2*>(smem_base + 16);
+    real2* const ws0 = stg + 4 * (size_t)row_elems;
+    const int ws_len = fused_ws_len(n);
+    const __half up2 = __float2half_rn(dm.up2);
+    const __half2 neg_s = __float2half2_rn(-dm.sharpen);
+    const __half hzero = __float2half_rn(0.f);
+    const real2* sp = spec + (size_t)c * dm.up_h * dm.spec_stride;
+    __half* oplane = out + (size_t)c * dm.out_plane;
+    __half* pplane = pre + (size_t)c * dm.pre_plane;
+    const int G = n / NP, g_last = G - 1;
+    __half corner_up[3] = {hzero, hzero, hzero};   // taps (n-3, n-2, n-1) of the row above the pending corner pixel
+    bool corner_pending = false;
+
+    auto store8 = [&](__half* dst, const __half2 (&o)[4]) {
+        const uint4 v = make_uint4(fused_h2u(o[0]), fused_h2u(o[1]), fused_h2u(o[2]), fused_h2u(o[3]));
+#if defined(__CUDA_ARCH__)
+        __stcs(reinterpret_cast<uint4*>(dst), v);
+#else
+        *reinterpret_cast<uint4*>(dst) = v;
+#endif
+    };
+    auto issue = [&](int pj, int buf) {
+        const real2* src = sp + (size_t)(2 * pj) * dm.spec_stride;
+        real2* dst = stg + (size_t)buf * 2 * row_elems;
+#if defined(B2R_HOST_EMU)
+        for (int e = 0; e < row_elems; ++e) { dst[e] = src[e]; dst[row_elems + e] = src[dm.spec_stride + e]; }
+#else
+        const unsigned bytes = (unsigned)(row_elems * sizeof(real2));
+        b2r_mbar_expect_tx(&bar[buf], 2 * bytes);
+        b2r_bulk_g2s(dst, src, bytes, &bar[buf]);
+        b2r_bulk_g2s(dst + row_elems, src + dm.spec_stride, bytes, &bar[buf]);
+#endif
+    };
+#if !defined(B2R_HOST_EMU)
+    if (tid == 0) { b2r_mbar_init(&bar[0], 1); b2r_mbar_init(&bar[1], 1); b2r_mbar_fence_init(); }
+    B2R_SYNC();
+#endif
+    if (tid == 0) issue(j0, 0);
+
+    for (int i = 0; i < S; ++i) {
+        const int j = j0 + i;
+        if (tid == 0 && i + 1 < S) issue(j + 1, (i + 1) & 1);
+#if defined(B2R_HOST_EMU)
+        B2R_SYNC();
+#else
+        b2r_mbar_wait(&bar[i & 1], (unsigned)((i >> 1) & 1));
+#endif
+        const real2* const sa = stg + (size_t)(i & 1) * 2 * row_elems;
+        real2* const wsc = ws0 + (i & 1) * ws_len;
+        __half* cur = reinterpret_cast<__half*>(wsc);                 // rows 2j (cur[0..n)) and 2j+1 (cur[n..2n))
+        const __half* prv = reinterpret_cast<const __half*>(ws0 + ((i & 1) ^ 1) * ws_len);
+        const int pre_mode = (i == 0 || i == S - 1) ? 1 : ((i == 1 || i == S - 2) ? 2 : 0);
+        const bool head = (i == 1), tail = (i == S - 2);
+        __half* p0 = pplane + (size_t)(2 * j) * n;
+        __half* p1 = p0 + n;
+        c2r_pair_emit<P, UP2, true, true>(plan, sa, sa + row_elems, wsc, tw, dm, tid, true, [&](int idx, real2 z) {
+            const __half v0 = __float2half_rn((float)(z.x * scale)), v1 = __float2half_rn((float)(z.y * scale));
+            cur[idx] = fused_tap_h(up2, v0);
+            cur[n + idx] = fused_tap_h(up2, v1);
+            if (pre_mode == 1) { p0[idx] = v0; p1[idx] = v1; }
+            else if (pre_mode == 2) {
+                if (head && idx == 0) p0[0] = v0;
+                if (tail && idx >= n - 3) p1[idx] = v1;
+            }
+        });
+        B2R_SYNC();
+        constexpr bool kShfl = (P::kT % 32 == 0);
+        constexpr int K = (P::kN / NP + P::kT - 1) / P::kT;
+        const __half* rowa = prv;
+        const __half* rowb = prv + n;
+        const __half* rowc = cur;
+        const __half* rowd = cur + n;
+        auto ld8 = [&](const __half* row, int x0) { return *reinterpret_cast<const uint4*>(row + x0); };
+        auto x_of = [&](int k) { const int g = k * T + tid; return (g < G ? g : g_last) * NP; };
+        // the pixel pair (n-2, n-1) of a row whose lower-right tap arrived one pair late
+        auto corner_pixel = [&](const __half (&u)[3], __half u_end, const __half* mid, __half m_end, const __half* dn, __half d_end, int y) {
+            CasRowH<2> tu, tm, td;
+            tu.b[0] = __halves2half2(u[1], u[2]); tu.link(u[0], u_end);
+            tm.b[0] = __halves2half2(mid[n - 2], mid[n - 1]); tm.link(mid[n - 3], m_end);
+            td.b[0] = __halves2half2(dn[n - 2], dn[n - 1]); td.link(dn[n - 3], d_end);
+            __half2 o1[1];
+            cas_row_f16<2>(tu, tm, td, neg_s, o1);
+            oplane[(size_t)y * n + n - 1] = __high2half(o1[0]);
+        };
+        if (i == 0) {
+            if (top) {
+#pragma unroll 1
+                for (int k = 0; k < K; ++k) {
+                    const bool valid = k * T + tid < G;
+                    const int x0 = x_of(k);
+                    CasRowH<NP> tc, td;
+                    __half2 o[4];
+                    fused_taps8h<kShfl>(rowc, ld8(rowc, x0), x0, n, rowc[n], tc);
+                    fused_taps8h<kShfl>(rowd, ld8(rowd, x0), x0, n, hzero, td);
+                    cas_row_f16<NP>(tc, tc, td, neg_s, o);
+                    if (valid) store8(oplane + x0, o);
+                }
+                corner_pending = true;
+                if (tid == g_last % T) { corner_up[0] = rowc[n - 3]; corner_up[1] = rowc[n - 2]; corner_up[2] = rowc[n - 1]; }
+            }
+        } else {
+            const int ya = 2 * j - 1, yb = 2 * j;
+            const __half end_a = rowa[n], end_b = rowc[0], end_c = rowc[n];
+            uint4 va = ld8(rowa, x_of(0)), vb = ld8(rowb, x_of(0)), vc = ld8(rowc, x_of(0)), vd = ld8(rowd, x_of(0));
+#pragma unroll
+            for (int k = 0; k < K; ++k) {
+                const bool valid = k * T + tid < G;
+                const int x0 = x_of(k);
+                uint4 na = va, nb = vb, nc = vc, nd = vd;
+                if (k + 1 < K) { const int x1 = x_of(k + 1); na = ld8(rowa, x1); nb = ld8(rowb, x1); nc = ld8(rowc, x1); nd = ld8(rowd, x1); }
+                CasRowH<NP> ta, tb, tc, td;
+                __half2 o[4];
+                fused_taps8h<kShfl>(rowa, va, x0, n, end_a, ta);
+                fused_taps8h<kShfl>(rowb, vb, x0, n, end_b, tb);
+                fused_taps8h<kShfl>(rowc, vc, x0, n, end_c, tc);
+                fused_taps8h<kShfl>(rowd, vd, x0, n, hzero, td);
+                cas_row_f16<NP>(ta, tb, tc, neg_s, o);
+                if (valid) store8(oplane + (size_t)ya * n + x0, o);
+                cas_row_f16<NP>(tb, tc, td, neg_s, o);
+                if (valid) store8(oplane + (size_t)yb * n + x0, o);
+                va = na; vb = nb; vc = nc; vd = nd;
+            }
+            if (tid == g_last % T) {
+                if (corner_pending)
+                    corner_pixel(corner_up, (yb - 2 == 0) ? rowa[n] : rowa[0], rowa, rowa[n], rowb, rowc[0], yb - 2);
+                corner_up[0] = rowb[n - 3]; corner_up[1] = rowb[n - 2]; corner_up[2] = rowb[n - 1];
+            }
+            corner_pending = true;
+        }
+        B2R_SYNC();
+    }
+}
+
+B2R_DEV void sharpen_fix_f16_impl(const __half* __restrict__ pre, __half* __restrict__ out, const FrameDims& dm,
+                                  const int* __restrict__ list) {
+    constexpr int NP = 8;
+    const int e = list[B2R_BID_Y];
+    const bool corner = (e & kFixCornerBit) != 0;
+    const int y = e & (kFixCornerBit - 1), ch = (int)B2R_BID_Z, n = dm.up_w;
+    const int x0 = (int)(B2R_BID_X * B2R_BDIM_X + B2R_TID_X) * NP;
+    if (x0 >= n) return;
+    if (corner && x0 + NP != n) return;
+    const __half* plane = pre + (size_t)ch * dm.pre_plane;
+    const __half2 up2 = __float2half2_rn(dm.up2), neg_s = __float2half2_rn(-dm.sharpen);
+    const int yu = y > 0 ? y - 1 : 0;
+    CasRowH<NP> t[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const __half* p = plane + (size_t)(r == 0 ? yu : y + r - 1) * n + x0;
+        const uint4 v = *reinterpret_cast<const uint4*>(p);
+        t[r].b[0] = cas_tap2(up2, fused_u2h(v.x)); t[r].b[1] = cas_tap2(up2, fused_u2h(v.y));
+        t[r].b[2] = cas_tap2(up2, fused_u2h(v.z)); t[r].b[3] = cas_tap2(up2, fused_u2h(v.w));
+        const __half2 ed = cas_tap2(up2, __halves2half2(p[x0 > 0 ? -1 : 0], p[NP]));   // flat +1 on the right
+        t[r].link(__low2half(ed), __high2half(ed));
+    }
+    __half2 o[4];
+    cas_row_f16<NP>(t[0], t[1], t[2], neg_s, o);
+    __half* dst = out + (size_t)ch * dm.out_plane + (size_t)y * n + x0;
+    if (corner) dst[NP - 1] = __high2half(o[3]);
+    else *reinterpret_cast<uint4*>(dst) = make_uint4(fused_h2u(o[0]), fused_h2u(o[1]), fused_h2u(o[2]), fused_h2u(o[3]));
+}
+template <int DUMMY>
+B2R_KERNEL k_sharpen_fix_f16(const __half* __restrict__ pre, __half* __restrict__ out, const FrameDims dm,
+                             const int* __restrict__ list) {
+    sharpen_fix_f16_impl(pre, out, dm, list);
+}
+
 #endif  // !B2R_REAL_IS_DOUBLE
 
 }  // namespace b2r

@@ -80,25 +80,36 @@ template <class P, int PPB> cudaError_t run_c2c(cudaStream_t s, const C2rArgs& a
 
 // ---- fused C2R + sharpen (b2r_fused.cuh): one CTA per strip of row pairs -----------------------------
 template <class P> cudaError_t prep_fused(int precision, int nx) {
-    if (precision != 0) return cudaErrorNotSupported;
+    if (precision != 0 && precision != 2) return cudaErrorNotSupported;
     const int n = (int)fused_smem_bytes(P::kN, nx);
     cudaError_t e;
+    if (precision == 2) {
+        if ((e = cudaFuncSetAttribute(k_c2r_sharpen_f16<P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, n))) return e;
+        return cudaFuncSetAttribute(k_c2r_sharpen_f16<P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, n);
+    }
     if ((e = cudaFuncSetAttribute(k_c2r_sharpen_f32<P, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, n))) return e;
     return cudaFuncSetAttribute(k_c2r_sharpen_f32<P, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, n);
 }
 template <class P> int fused_per_sm(int precision, int nx) {
-    if (precision != 0) return 0;
+    if (precision != 0 && precision != 2) return 0;
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_c2r_sharpen_f32<P, true>, P::kT, fused_smem_bytes(P::kN, nx)) != cudaSuccess) return 0;
-    return per_sm;
+    const size_t smem = fused_smem_bytes(P::kN, nx);
+    cudaError_t e = precision == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_c2r_sharpen_f16<P, true>, P::kT, smem)
+                                   : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_c2r_sharpen_f32<P, true>, P::kT, smem);
+    return e == cudaSuccess ? per_sm : 0;
 }
 template <class P> cudaError_t run_fused(cudaStream_t s, const FusedArgs& a) {
-    if (a.precision != 0) return cudaErrorNotSupported;
+    if (a.precision != 0 && a.precision != 2) return cudaErrorNotSupported;
     const bool up2 = (a.dm.up_w == 2 * a.dm.w);
     const size_t smem = fused_smem_bytes(P::kN, a.dm.nx);
     const int grid = 3 * a.nsp;
-    if (up2) k_c2r_sharpen_f32<P, true><<<grid, P::kT, smem, s>>>(a.spec, (float*)a.out, (float*)a.pre, a.tw, P{}, a.dm, a.scale, a.nsp);
-    else k_c2r_sharpen_f32<P, false><<<grid, P::kT, smem, s>>>(a.spec, (float*)a.out, (float*)a.pre, a.tw, P{}, a.dm, a.scale, a.nsp);
+    if (a.precision == 2) {
+        if (up2) k_c2r_sharpen_f16<P, true><<<grid, P::kT, smem, s>>>(a.spec, (__half*)a.out, (__half*)a.pre, a.tw, P{}, a.dm, a.scale, a.nsp);
+        else k_c2r_sharpen_f16<P, false><<<grid, P::kT, smem, s>>>(a.spec, (__half*)a.out, (__half*)a.pre, a.tw, P{}, a.dm, a.scale, a.nsp);
+    } else {
+        if (up2) k_c2r_sharpen_f32<P, true><<<grid, P::kT, smem, s>>>(a.spec, (float*)a.out, (float*)a.pre, a.tw, P{}, a.dm, a.scale, a.nsp);
+        else k_c2r_sharpen_f32<P, false><<<grid, P::kT, smem, s>>>(a.spec, (float*)a.out, (float*)a.pre, a.tw, P{}, a.dm, a.scale, a.nsp);
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     return launch_sharpen_fix(s, a);

@@ -435,6 +435,11 @@ struct Pipeline {
                 cv.notify_all();
             } else {
                 auto t0 = clk::now();
+                if (!s.in) {   // first use of this ring slot
+                    s.in = (unsigned char*)b2r_host_alloc((size_t)3 * w * h);
+                    s.out = (unsigned char*)b2r_host_alloc((size_t)3 * info.up_w * info.up_h);
+                    if (!s.in || !s.out) { printf("pinned allocation failed: %s\n", b2r_last_error()); fail_with(-4); return; }
+                }
                 snprintf(name, sizeof name, "%s/%06u.png", cfg.ifolder, file_of(k));
                 int w2 = 0, h2 = 0;
                 if (!png::load_rgb(name, nullptr, &w2, &h2, &err, s.in, (size_t)w * h * 3)) {
@@ -480,19 +485,19 @@ struct Pipeline {
         info.up_w = (uint32_t)(cfg.upscale * (float)w); info.up_h = (uint32_t)(cfg.upscale * (float)h);
         const uint32_t lanes = std::max(1u, std::min(cfg.lanes, 8u));
         const size_t n_slots = std::min<size_t>(total, (size_t)cfg.num_threads + 2 * lanes + 2);
-        slots.resize(n_slots);
-        for (auto& s : slots) {
-            s.in = (unsigned char*)b2r_host_alloc((size_t)3 * w * h);
-            s.out = (unsigned char*)b2r_host_alloc((size_t)3 * info.up_w * info.up_h);
-            if (!s.in || !s.out) { printf("pinned allocation failed: %s\n", b2r_last_error()); return -4; }
-        }
+        slots.resize(n_slots);   // pinned buffers are allocated by the codec worker that first decodes into a slot (in parallel)
         at_ring = since_start();
         std::vector<std::thread> th;
         th.emplace_back([this] { int rc = create_plan(); if (rc) fail_with(rc); else submit_loop(); });
         for (uint32_t t = 0; t < cfg.num_threads; ++t) th.emplace_back([this] { worker_loop(); });
         for (auto& t : th) t.join();
         if (plan) b2r_synchronize(plan);
-        for (auto& s : slots) { b2r_host_free(s.in); b2r_host_free(s.out); }
+        {   // release the ring in parallel (page unpinning is the slow part)
+            std::vector<std::thread> fr;
+            for (size_t t0 = 0; t0 < slots.size(); t0 += 4)
+                fr.emplace_back([this, t0] { for (size_t i = t0; i < std::min(t0 + 4, slots.size()); ++i) { b2r_host_free(slots[i].in); b2r_host_free(slots[i].out); } });
+            for (auto& t : fr) t.join();
+        }
         char dev_name[256] = "";
         b2r_device_name(device, dev_name, sizeof dev_name);
         printf("GPU %d finished: %u frames, codec thread-seconds: decode %.2f, encode %.2f, waiting for the GPU %.2f. Device name: %s API:%s\n",
