@@ -391,11 +391,13 @@ int build(b2r_plan* p) {
                   ppp >= 6 && fused_smem_bytes(g.up_w, g.nx) <= smem_max;
         if (ok && p->k_c2r.prepare_fused(g.precision, g.nx) != cudaSuccess) { (void)cudaGetLastError(); ok = false; }
         if (ok) {
-            // measured on B200 (profiles/): the fused kernel wins while two strip CTAs fit one SM (4096- and 3840-wide
-            // rows: +5 % sustained, half the HBM traffic, no power-cap throttling); with a single resident CTA
-            // (7680-wide rows) the separate kernels are faster (307 vs 349 us).  B2R_FUSED=2 forces it.
+            // measured on B200 (profiles/README.md): the fused kernel wins for fp32 while two strip CTAs fit one SM
+            // (4096- and 3840-wide rows: +5 % sustained, half the HBM traffic, no power-cap throttling); with a single
+            // resident CTA (7680-wide rows: 349 vs 307 us) and for fp16 storage (whose stand-alone sharpen moves half
+            // the bytes: c4 80 vs 64 us) the separate kernels are faster.  B2R_FUSED=2 forces the fused kernel.
             const int per_sm = p->k_c2r.fused_blocks_per_sm(g.precision, g.nx);
-            if (per_sm >= 2 || (per_sm >= 1 && env_int("B2R_FUSED", 1) == 2)) {
+            const bool forced = env_int("B2R_FUSED", 1) == 2;
+            if ((per_sm >= 2 && g.precision == 0) || (per_sm >= 1 && forced)) {
                 const int slots = prop.multiProcessorCount * per_sm;
                 int nsp = env_int("B2R_FUSED_NSP", 0);
                 if (nsp <= 0) nsp = std::max(1, slots / 3);          // one wave of strip CTAs over the three planes
