@@ -6,8 +6,10 @@ tag=${1:-r2}
 mkdir -p gpurun_out
 run() {  # name w h prec [env...]
   name=$1; w=$2; h=$3; p=$4; shift 4
-  env "$@" ncu --set full --clock-control none --import-source on -s 20 -c 4 -o gpurun_out/prof_${tag}_${name} -f \
+  env "$@" ncu --set full --clock-control none -s 20 -c 4 -o /tmp/prof_${tag}_${name} -f \
       python scripts/quick_time.py $w $h $p > gpurun_out/ncu_${tag}_${name}.log 2>&1
+  # only the raw metric table travels back (gpurun merges at most 64 MiB; a --set full report is ~15 MB)
+  ncu -i /tmp/prof_${tag}_${name}.ncu-rep --page raw --csv 2>/dev/null | gzip > gpurun_out/prof_${tag}_${name}.raw.csv.gz
 }
 run c2 2048 1024 0
 run c2_separate 2048 1024 0 B2R_FUSED=0

@@ -1,6 +1,10 @@
 """print the warp stall breakdown (cycles stalled per issued instruction) of every kernel in an ncu report"""
 import csv, io, subprocess, sys
-txt = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+if sys.argv[1].endswith(".csv.gz"):
+    import gzip
+    txt = gzip.open(sys.argv[1], "rt").read()
+else:
+    txt = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(txt)))
 hdr = rows[0]
 ki = hdr.index("Kernel Name")

@@ -30,7 +30,11 @@ SHORT = {"k_r2c_rows": "r2c_rows", "k_cols": "cols", "k_c2r_sharpen": "c2r_sharp
 
 def main():
     rep, out, cfg = sys.argv[1], sys.argv[2], (sys.argv[3] if len(sys.argv) > 3 else "c2")
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv.gz"):      # the raw page exported on the GPU box (scripts/collect_ncu.sh)
+        import gzip
+        txt = gzip.open(rep, "rt").read()
+    else:
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     hdr, units = rows[0], rows[1]
     ki = hdr.index("Kernel Name")

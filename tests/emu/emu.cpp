@@ -183,6 +183,7 @@ template <class P, int PPB> static void emu_c2r(FrameCtx& c, const P plan, const
     });
 }
 static int g_cols_grouped = 0;   // opt-in like the product (B2R_COLS_GROUPED=1)
+static int g_cols_staged = 0;    // the persistent, asynchronously staged column kernel (B2R_COLS_STAGED=1)
 static int g_fused_nsp = 0;      // > 0: K7 + K8 through the fused strip kernel (b2r_fused.cuh) with this many strips per plane
 
 // fused C2R + sharpen + boundary fix-up, as launch_frame / run_fused do it (fp32 / fp16, static schedules)
@@ -203,12 +204,9 @@ template <class P> static void emu_fused(FrameCtx& c, const P plan, const HostFf
         }
     });
     std::vector<int> fix;
-    for (int q = 1; q < nsp; ++q) {
-        const int b = 2 * fused_strip_begin(q, nsp, ppp);
-        fix.push_back((b - 2) | kFixCornerBit); fix.push_back(b - 1); fix.push_back(b);
-    }
-    fix.push_back((c.g.up_h - 2) | kFixCornerBit); fix.push_back(c.g.up_h - 1);
-    Dim3 g2, b2; b2.x = 32; g2.x = (c.g.up_w / (half ? 8 : 4) + 31) / 32; g2.y = (unsigned)fix.size(); g2.z = 3;
+    for (int q = 1; q < nsp; ++q) fix.push_back(2 * fused_strip_begin(q, nsp, ppp));
+    fix.push_back(c.g.up_h);
+    Dim3 g2, b2; b2.x = 32; g2.x = (c.g.up_w / 8 + 31) / 32; g2.y = (unsigned)fix.size(); g2.z = 3;
     b2r_emu::launch(g2, b2, 0, [&] {
         if (half) k_sharpen_fix_f16<0>((const __half*)c.pre.data(), (__half*)out, c.dm, fix.data());
         else k_sharpen_fix_f32<0>((const float*)c.pre.data(), (float*)out, c.dm, fix.data());
@@ -221,6 +219,14 @@ static void emu_cols(FrameCtx& c, const PF pf, const PI pi, const HostFft& hf, c
     const float2 *twf = hf.twiddles.data(), *twi = hi.twiddles.data();
     const float scale = 1.0f / (float)c.g.up_h;
     if constexpr (PI::kStatic) {
+        if (g_cols_staged) {
+            Dim3 g2, b2; b2.x = CC * hi.desc.threads; g2.x = 5;   // few persistent CTAs, several tiles each
+            const int tiles_per_ch = (c.g.nx + CC - 1) / CC;
+            b2r_emu::launch(g2, b2, cols_staged_smem_bytes(c.g.h, c.g.up_h, CC, sizeof(float2)), [&] {
+                k_cols_staged<PF, PI, CC>(c.spec1.data(), c.spec2.data(), twf, twi, pf, pi, c.dm, scale, g_c2c ? c.nyq.data() : nullptr, tiles_per_ch);
+            });
+            return;
+        }
         if constexpr (PI::kT % 32 == 0 && PF::kStages >= 2 && PI::kStages >= 3) {
             if (g_cols_grouped) {
                 b2r_emu::launch(grid, block, (size_t)CC * cols_group_stride(c.g.up_h) * sizeof(float2), [&] {
@@ -293,6 +299,7 @@ void b2r_emu_set_c2r_bulk(int on) { g_c2r_bulk = on; }
 void b2r_emu_set_r2c_bulk(int on) { g_r2c_bulk = on; }
 void b2r_emu_set_c2c(int on) { g_c2c = on; }
 void b2r_emu_set_cols_grouped(int on) { g_cols_grouped = on; }
+void b2r_emu_set_cols_staged(int on) { g_cols_staged = on; }
 void b2r_emu_set_fused(int nsp) { g_fused_nsp = nsp; }
 void b2r_emu_set_sharpen_fast(int on) { g_sharpen_fast = on; }
 

@@ -366,3 +366,21 @@ def test_r2c_bulk_kernel_equals_direct_kernel(w, h, prec):
     assert a["used_static"] & 1 and b["used_static"] & 1
     assert np.array_equal(a["spec1"].view(np.uint64), b["spec1"].view(np.uint64))
     assert np.array_equal(a["out"].view(np.uint8), b["out"].view(np.uint8))
+
+
+@pytest.mark.parametrize("w,h", [(256, 128), (24, 512), (60, 360)])
+def test_cols_staged_kernel_equals_direct_kernel(w, h):
+    """the persistent column kernel whose next tile is staged by asynchronous copies (k_cols_staged) writes the same
+    column spectra, bit for bit, as the one-tile-per-CTA kernel -- including the last, partially valid tile of a
+    plane (zero-filled columns) and CTAs that run several tiles"""
+    plan = vo.make_plan(w, h, 2.0)
+    x = vo.synthetic_frame("noise", w, h, 13)
+    L = eu.lib()
+    a = eu.frame(x, 2.0, 0, 0.2, plan)
+    L.b2r_emu_set_cols_staged(1)
+    try:
+        b = eu.frame(x, 2.0, 0, 0.2, plan)
+    finally:
+        L.b2r_emu_set_cols_staged(0)
+    assert a["used_static"] & 2 and b["used_static"] & 2
+    assert np.array_equal(a["spec2"].view(np.uint64), b["spec2"].view(np.uint64))

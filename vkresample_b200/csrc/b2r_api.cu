@@ -449,14 +449,8 @@ int build(b2r_plan* p) {
     if (p->fused_nsp > 0) {   // rows k_sharpen_fix finishes, per plane (b2r_fused.cuh)
         std::vector<int> fix;
         const int ppp = g.up_h / 2, nsp = p->fused_nsp;
-        for (int q = 1; q < nsp; ++q) {
-            const int b = 2 * fused_strip_begin(q, nsp, ppp);        // first row of strip q
-            fix.push_back((b - 2) | kFixCornerBit);
-            fix.push_back(b - 1);
-            fix.push_back(b);
-        }
-        fix.push_back((g.up_h - 2) | kFixCornerBit);                 // plane end: the row below is the pad region
-        fix.push_back(g.up_h - 1);
+        for (int q = 1; q < nsp; ++q) fix.push_back(2 * fused_strip_begin(q, nsp, ppp));   // first row of strip q
+        fix.push_back(g.up_h);                                       // plane end: the row below is the pad region
         p->n_fix = (int)fix.size();
         CU(cudaMalloc((void**)&p->d_fix, fix.size() * sizeof(int)));
         CU(cudaMemcpy(p->d_fix, fix.data(), fix.size() * sizeof(int), cudaMemcpyHostToDevice));

@@ -32,8 +32,8 @@ B2R_HD constexpr int fused_ws_len(int n) { return (smem_padded_len(n) + 1) & ~1;
 B2R_HD constexpr size_t fused_smem_bytes(int n, int nx) {
     return 16 + 4 * (size_t)c2r_stage_row_elems(nx) * sizeof(real2) + 2 * (size_t)fused_ws_len(n) * sizeof(real2);
 }
-// fix-up list entry: output row y, or only its last pixel
-constexpr int kFixCornerBit = 1 << 30;
+// fix-up list: one entry per strip boundary of a plane = the first row of the lower strip; the plane's end is
+// the entry upH (b2r_api.cu builds it; the same list serves the three planes)
 // register budget per thread: 128 with one butterfly per thread in every stage (two 256-thread CTAs per SM),
 // 168 when a thread holds more than 16 complex values
 template <class P> constexpr int fused_min_blocks() {
@@ -226,42 +226,61 @@ k_c2r_sharpen_f32(const real2* __restrict__ spec, float* __restrict__ out, float
     }
 }
 
-// Rows (or single last pixels) the fused kernel leaves out, finished from the raw values it stored in the
-// pre-sharpen buffer.  grid = (ceil(upW/4/blockDim.x), entries per plane, 3); list: entries of one plane
-// (the same for all three), y | kFixCornerBit for "last pixel only".
+// Rows (and single last pixels) the fused kernel leaves out, finished from the raw values it stored in the
+// pre-sharpen buffer.  One list entry = one strip boundary b (the first row of the lower strip; b == upH for the
+// plane's end): a thread loads its 8 columns of rows b-2 .. b+1 once and produces rows b-1 and b (only b-1 at
+// the plane's end); the thread that owns the rows' last pixels also redoes pixel (upW-1, b-2), whose lower-right
+// tap is row b's first element.  grid = (ceil(upW/8/blockDim.x), boundaries per plane, 3).
 B2R_DEV void sharpen_fix_f32_impl(const float* __restrict__ pre, float* __restrict__ out, const FrameDims& dm,
                                   const int* __restrict__ list) {
-    constexpr int NP = 4;
-    const int e = list[B2R_BID_Y];
-    const bool corner = (e & kFixCornerBit) != 0;
-    const int y = e & (kFixCornerBit - 1), ch = (int)B2R_BID_Z, n = dm.up_w;
+    constexpr int NP = 8;
+    const int b = list[B2R_BID_Y], ch = (int)B2R_BID_Z, n = dm.up_w;
     const int x0 = (int)(B2R_BID_X * B2R_BDIM_X + B2R_TID_X) * NP;
     if (x0 >= n) return;
-    if (corner && x0 + NP != n) return;
     const float* plane = pre + (size_t)ch * dm.pre_plane;
+    float* oplane = out + (size_t)ch * dm.out_plane;
     const float up2 = dm.up2, neg_s = -dm.sharpen;
-    const int yu = y > 0 ? y - 1 : 0;
-    float t[3][NP + 2];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        const float* p = plane + (size_t)(r == 0 ? yu : y + r - 1) * n + x0;
-        const float4 v = *reinterpret_cast<const float4*>(p);
-        t[r][1] = cas_tap(up2, v.x); t[r][2] = cas_tap(up2, v.y); t[r][3] = cas_tap(up2, v.z); t[r][4] = cas_tap(up2, v.w);
-        t[r][0] = (x0 > 0) ? cas_tap(up2, p[-1]) : t[r][1];
-        t[r][NP + 1] = cas_tap(up2, p[NP]);     // flat +1
+    const bool plane_end = (b >= dm.up_h);
+    // clamped magnitudes of columns x0-1 .. x0+8 of row y (flat +1 on the right, clamp on the left)
+    auto taps = [&](int y, float (&t)[NP + 2]) {
+        const float* p = plane + (size_t)y * n + x0;
+        const float4 v0 = *reinterpret_cast<const float4*>(p), v1 = *reinterpret_cast<const float4*>(p + 4);
+        t[1] = cas_tap(up2, v0.x); t[2] = cas_tap(up2, v0.y); t[3] = cas_tap(up2, v0.z); t[4] = cas_tap(up2, v0.w);
+        t[5] = cas_tap(up2, v1.x); t[6] = cas_tap(up2, v1.y); t[7] = cas_tap(up2, v1.z); t[8] = cas_tap(up2, v1.w);
+        t[0] = (x0 > 0) ? cas_tap(up2, p[-1]) : t[1];
+        t[NP + 1] = cas_tap(up2, p[NP]);
+    };
+    auto store8 = [&](int y, const float (&o)[NP]) {
+        float* dst = oplane + (size_t)y * n + x0;
+        *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(o[4], o[5], o[6], o[7]);
+    };
+    float ta[NP + 2], tb[NP + 2], tc[NP + 2], td[NP + 2], o[NP];
+    taps(b - 2, ta);
+    taps(b - 1, tb);
+    taps(b, tc);                       // at the plane's end: the zero pad region below the plane
+    cas_row_f32<NP>(ta, tb, tc, neg_s, o);
+    store8(b - 1, o);
+    if (!plane_end) {
+        taps(b + 1, td);
+        cas_row_f32<NP>(tb, tc, td, neg_s, o);
+        store8(b, o);
     }
-    float o[NP];
-    cas_row_f32<NP>(t[0], t[1], t[2], neg_s, o);
-    float* dst = out + (size_t)ch * dm.out_plane + (size_t)y * n + x0;
-    if (corner) dst[NP - 1] = o[NP - 1];
-    else *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+    if (x0 + NP == n) {                // pixel (n-1, b-2): rows b-3 (two elements were stored), b-2, b-1
+        const float* pu = plane + (size_t)(b - 3) * n;
+        float up3[3] = {cas_tap(up2, pu[n - 2]), cas_tap(up2, pu[n - 1]), cas_tap(up2, pu[n])};
+        float mid3[3] = {ta[NP - 1], ta[NP], ta[NP + 1]};
+        float dn3[3] = {tb[NP - 1], tb[NP], tb[NP + 1]};
+        float o1[1];
+        cas_row_f32<1>(up3, mid3, dn3, neg_s, o1);
+        oplane[(size_t)(b - 2) * n + n - 1] = o1[0];
+    }
 }
 template <int DUMMY>
 B2R_KERNEL k_sharpen_fix_f32(const float* __restrict__ pre, float* __restrict__ out, const FrameDims dm,
                              const int* __restrict__ list) {
     sharpen_fix_f32_impl(pre, out, dm, list);
 }
-
 
 // ---- fp16 storage (precision 2) ---------------------------------------------------------------------
 // Same strip structure; the rows are kept as HALF clamped magnitudes (the reference's sharpen shader computes
@@ -452,30 +471,47 @@ k_c2r_sharpen_f16(const real2* __restrict__ spec, __half* __restrict__ out, __ha
 B2R_DEV void sharpen_fix_f16_impl(const __half* __restrict__ pre, __half* __restrict__ out, const FrameDims& dm,
                                   const int* __restrict__ list) {
     constexpr int NP = 8;
-    const int e = list[B2R_BID_Y];
-    const bool corner = (e & kFixCornerBit) != 0;
-    const int y = e & (kFixCornerBit - 1), ch = (int)B2R_BID_Z, n = dm.up_w;
+    const int b = list[B2R_BID_Y], ch = (int)B2R_BID_Z, n = dm.up_w;
     const int x0 = (int)(B2R_BID_X * B2R_BDIM_X + B2R_TID_X) * NP;
     if (x0 >= n) return;
-    if (corner && x0 + NP != n) return;
     const __half* plane = pre + (size_t)ch * dm.pre_plane;
+    __half* oplane = out + (size_t)ch * dm.out_plane;
     const __half2 up2 = __float2half2_rn(dm.up2), neg_s = __float2half2_rn(-dm.sharpen);
-    const int yu = y > 0 ? y - 1 : 0;
-    CasRowH<NP> t[3];
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        const __half* p = plane + (size_t)(r == 0 ? yu : y + r - 1) * n + x0;
+    const bool plane_end = (b >= dm.up_h);
+    auto taps = [&](int y, CasRowH<NP>& t) {
+        const __half* p = plane + (size_t)y * n + x0;
         const uint4 v = *reinterpret_cast<const uint4*>(p);
-        t[r].b[0] = cas_tap2(up2, fused_u2h(v.x)); t[r].b[1] = cas_tap2(up2, fused_u2h(v.y));
-        t[r].b[2] = cas_tap2(up2, fused_u2h(v.z)); t[r].b[3] = cas_tap2(up2, fused_u2h(v.w));
+        t.b[0] = cas_tap2(up2, fused_u2h(v.x)); t.b[1] = cas_tap2(up2, fused_u2h(v.y));
+        t.b[2] = cas_tap2(up2, fused_u2h(v.z)); t.b[3] = cas_tap2(up2, fused_u2h(v.w));
         const __half2 ed = cas_tap2(up2, __halves2half2(p[x0 > 0 ? -1 : 0], p[NP]));   // flat +1 on the right
-        t[r].link(__low2half(ed), __high2half(ed));
-    }
+        t.link(__low2half(ed), __high2half(ed));
+    };
+    auto store8 = [&](int y, const __half2 (&o)[4]) {
+        *reinterpret_cast<uint4*>(oplane + (size_t)y * n + x0) = make_uint4(fused_h2u(o[0]), fused_h2u(o[1]), fused_h2u(o[2]), fused_h2u(o[3]));
+    };
+    CasRowH<NP> ta, tb, tc, td;
     __half2 o[4];
-    cas_row_f16<NP>(t[0], t[1], t[2], neg_s, o);
-    __half* dst = out + (size_t)ch * dm.out_plane + (size_t)y * n + x0;
-    if (corner) dst[NP - 1] = __high2half(o[3]);
-    else *reinterpret_cast<uint4*>(dst) = make_uint4(fused_h2u(o[0]), fused_h2u(o[1]), fused_h2u(o[2]), fused_h2u(o[3]));
+    taps(b - 2, ta);
+    taps(b - 1, tb);
+    taps(b, tc);
+    cas_row_f16<NP>(ta, tb, tc, neg_s, o);
+    store8(b - 1, o);
+    if (!plane_end) {
+        taps(b + 1, td);
+        cas_row_f16<NP>(tb, tc, td, neg_s, o);
+        store8(b, o);
+    }
+    if (x0 + NP == n) {                // pixel (n-1, b-2)
+        const __half* pu = plane + (size_t)(b - 3) * n;
+        CasRowH<2> tu, tm, tdn;
+        const __half2 u01 = cas_tap2(up2, __halves2half2(pu[n - 2], pu[n - 1])), u2e = cas_tap2(up2, __halves2half2(pu[n - 3], pu[n]));
+        tu.b[0] = u01; tu.link(__low2half(u2e), __high2half(u2e));
+        tm.b[0] = ta.b[3]; tm.link(__high2half(ta.b[2]), __high2half(ta.a[4]));
+        tdn.b[0] = tb.b[3]; tdn.link(__high2half(tb.b[2]), __high2half(tb.a[4]));
+        __half2 o1[1];
+        cas_row_f16<2>(tu, tm, tdn, neg_s, o1);
+        oplane[(size_t)(b - 2) * n + n - 1] = __high2half(o1[0]);
+    }
 }
 template <int DUMMY>
 B2R_KERNEL k_sharpen_fix_f16(const __half* __restrict__ pre, __half* __restrict__ out, const FrameDims dm,

@@ -44,7 +44,7 @@ static cudaError_t launch_sharpen_fast(cudaStream_t s, const SharpenArgs& a) {
 cudaError_t launch_sharpen_fix(cudaStream_t s, const FusedArgs& a) {
     if (a.n_fix <= 0) return cudaSuccess;
     if (a.precision != 0 && a.precision != 2) return cudaErrorNotSupported;
-    const int groups = a.dm.up_w / (a.precision == 2 ? 8 : 4), bx = 128;
+    const int groups = a.dm.up_w / 8, bx = 128;   // 8 pixels per thread in both precisions
     dim3 block(bx), grid((groups + bx - 1) / bx, a.n_fix, 3);
     if (a.precision == 2) k_sharpen_fix_f16<0><<<grid, block, 0, s>>>((const __half*)a.pre, (__half*)a.out, a.dm, a.fix_list);
     else k_sharpen_fix_f32<0><<<grid, block, 0, s>>>((const float*)a.pre, (float*)a.out, a.dm, a.fix_list);
