@@ -278,6 +278,10 @@ def run_b200(args):
     plan.timer_start(); run_frames(plan, 640); ms_b = allmax(plan.timer_stop())
     burst = {"value": world * 640 / (ms_b * 1e-3), "unit": UNIT, "frames": 640, "timed_region_s": ms_b * 1e-3}
 
+    # ---- per-kernel device time for the roofline (events between kernels, same plan and workload, directly after
+    # the timed region: later legs create further plans and pinned buffers)
+    pk = plan.profile_kernels(20)
+
     # ---- the same device-resident measurement with B2R_FLAG_EXACT_SHARPEN (bit-exact sharpen kernels);
     # reported beside the headline, never instead of it
     exact = None
@@ -300,6 +304,22 @@ def run_b200(args):
                      "flag": "B2R_FLAG_EXACT_SHARPEN", "sharpen_us": round(pkx["sharpen"] * 1e3, 2),
                      "max_abs_default_vs_exact_output": diff}
             del scratch
+
+    # ---- when the plan runs the fused C2R + sharpen kernel: the same workload with the two kernels kept apart
+    # (B2R_FLAG_SEPARATE_SHARPEN), for the per-kernel roofline of the pieces the fused kernel replaced
+    separate = None
+    if int(plan.info.fused_strips_per_plane) > 0 and not args.no_exact_leg:
+        with vb.Plan(w, h, up, prec, s, device=local, flags=plan_flags | vb.FLAG_SEPARATE_SHARPEN) as ps:
+            ps.set_lanes(args.lanes)
+            n_s = max(ring, min(F * args.steps, 2048))
+            run_frames(ps, 3 * ring)
+            ps.synchronize()
+            barrier()
+            ps.timer_start(); run_frames(ps, n_s); ms_s = allmax(ps.timer_stop())
+            barrier()
+            pks = ps.profile_kernels(20)
+            separate = {"value": world * n_s / (ms_s * 1e-3), "unit": UNIT, "frames": n_s, "flag": "B2R_FLAG_SEPARATE_SHARPEN",
+                        "kernel_us": {k: round(v * 1e3, 2) for k, v in pks.items()}}
 
     # ---- end to end through the C-ABI with pinned HOST buffers: per frame H2D + frame + D2H, frames
     # rotating over the plan's lanes so that the copies of one frame overlap the kernels of another.
@@ -365,8 +385,7 @@ def run_b200(args):
 
     result_checksum = float(np.frombuffer(h_out[0].numpy().tobytes()[:4096], dtype=np_dt).astype(np.float64).sum())
 
-    # ---- roofline of the dominant kernel (separate pass, events between kernels, same workload)
-    pk = plan.profile_kernels(20)
+    # ---- roofline of the dominant kernel
     alg = kernel_algorithmic_bytes(w, h, plan.up_w, plan.up_h, elem)
     if int(plan.info.fused_strips_per_plane) > 0:   # fused C2R + sharpen (+ boundary-row fix-up): no pre-sharpen plane
         pk = {"r2c_rows": pk["r2c_rows"], "cols": pk["cols"], "c2r_sharpen": pk["c2r_rows"]}
@@ -380,6 +399,14 @@ def run_b200(args):
         traffic = tj.get(args.config, {}).get(dom)
     except Exception:
         pass
+    # the fused kernel is issue-bound, not HBM-bound: its instruction count (ncu, profiles/r2_ncu_c2.md) against
+    # the SM issue rate is reported beside the byte roofline
+    issue = None
+    if dom == "c2r_sharpen" and args.config == "c2":
+        winst = 47.2e6
+        t_issue = winst / (148 * 4 * 1.965e9)
+        issue = {"warp_instructions_per_launch": winst, "issue_limit_us": round(t_issue * 1e6, 1),
+                 "frac_of_issue_limit": round(t_issue / (pk[dom] * 1e-3), 3), "source": "ncu smsp__inst_executed.sum, profiles/r2_ncu_c2.md"}
     roofline = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg[dom],
@@ -387,6 +414,8 @@ def run_b200(args):
                 "kernel_frac": {k: round(alg[k] / (v * 1e-3) / 1e9 / peak, 4) for k, v in pk.items()},
                 "frame_algorithmic_gbs": alg["frame"] * value / world / 1e9,
                 "frame_frac": alg["frame"] * value / world / 1e9 / peak}
+    if issue:
+        roofline["issue"] = issue
 
     if rank == 0:
         cpu = None
@@ -434,6 +463,9 @@ def run_b200(args):
                 "burst": burst, "roofline": roofline, "clocks": clocks}
         if exact:
             line["exact_sharpen"] = exact
+        if separate:
+            separate["kernel_frac"] = {k: round(alg[k] / (v * 1e-6) / 1e9 / peak, 4) for k, v in separate["kernel_us"].items()}
+            line["separate_kernels"] = separate
         if cpu:
             line["cpu_baseline"] = cpu
         emit(line)
