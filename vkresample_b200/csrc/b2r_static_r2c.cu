@@ -39,7 +39,9 @@ template <class P, class TIn> cudaError_t run_bulk_t(cudaStream_t s, const R2cAr
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_r2c_rows_bulk<P, TIn>, P::kT, smem);
     if (e != cudaSuccess) return e;
     const int slots = sms * (per_sm > 0 ? per_sm : 1);
-    const int trips = (pairs + slots - 1) / slots;           // every CTA runs `trips` (or trips-1) pairs
+    static const int min_trips = [] { const char* e = getenv("B2R_R2C_TRIPS"); return e ? atoi(e) : 0; }();   // tuning aid
+    int trips = (pairs + slots - 1) / slots;                 // every CTA runs `trips` (or trips-1) pairs
+    if (min_trips > trips) trips = min_trips;
     const int grid = (pairs + trips - 1) / trips;
     k_r2c_rows_bulk<P, TIn><<<grid, P::kT, smem, s>>>((const TIn*)a.in, a.spec, a.tw, P{}, a.dm, pairs);
     return cudaGetLastError();
