@@ -184,6 +184,7 @@ template <class P, int PPB> static void emu_c2r(FrameCtx& c, const P plan, const
 }
 static int g_cols_grouped = 0;   // opt-in like the product (B2R_COLS_GROUPED=1)
 static int g_cols_staged = 0;    // the persistent, asynchronously staged column kernel (B2R_COLS_STAGED=1)
+static int g_cols_2x = 0;        // the exact-2x column kernel (k_cols2x), as the product uses for upH == 2H
 static int g_fused_nsp = 0;      // > 0: K7 + K8 through the fused strip kernel (b2r_fused.cuh) with this many strips per plane
 
 // fused C2R + sharpen + boundary fix-up, as launch_frame / run_fused do it (fp32 / fp16, static schedules)
@@ -219,6 +220,21 @@ static void emu_cols(FrameCtx& c, const PF pf, const PI pi, const HostFft& hf, c
     const float2 *twf = hf.twiddles.data(), *twi = hi.twiddles.data();
     const float scale = 1.0f / (float)c.g.up_h;
     if constexpr (PI::kStatic) {
+        if constexpr (PI::kN == 2 * PF::kN) {
+            if (g_cols_2x) {
+                std::vector<float2> ramp((size_t)c.g.h);
+                for (int k = 0; k < c.g.h; ++k) {
+                    const int ks = (k < c.g.h / 2) ? k : k - c.g.h;
+                    const double a = 3.14159265358979323846 * (double)ks / (double)c.g.h;
+                    ramp[(size_t)k] = make_float2((float)std::cos(a), (float)std::sin(a));
+                }
+                Dim3 g2, b2; b2.x = CC * hf.desc.threads; g2.x = (c.g.nx + CC - 1) / CC; g2.y = 3;
+                b2r_emu::launch(g2, b2, smem_padded_len(c.g.h * CC) * sizeof(float2), [&] {
+                    k_cols2x<PF, CC>(c.spec1.data(), c.spec2.data(), twf, ramp.data(), pf, c.dm, scale, g_c2c ? c.nyq.data() : nullptr);
+                });
+                return;
+            }
+        }
         if (g_cols_staged) {
             Dim3 g2, b2; b2.x = CC * hi.desc.threads; g2.x = 5;   // few persistent CTAs, several tiles each
             const int tiles_per_ch = (c.g.nx + CC - 1) / CC;
@@ -300,6 +316,7 @@ void b2r_emu_set_r2c_bulk(int on) { g_r2c_bulk = on; }
 void b2r_emu_set_c2c(int on) { g_c2c = on; }
 void b2r_emu_set_cols_grouped(int on) { g_cols_grouped = on; }
 void b2r_emu_set_cols_staged(int on) { g_cols_staged = on; }
+void b2r_emu_set_cols_2x(int on) { g_cols_2x = on; }
 void b2r_emu_set_fused(int nsp) { g_fused_nsp = nsp; }
 void b2r_emu_set_sharpen_fast(int on) { g_sharpen_fast = on; }
 

@@ -33,6 +33,7 @@ def lib():
         L.b2r_emu_set_fused.argtypes = [ctypes.c_int]
         L.b2r_emu_set_r2c_bulk.argtypes = [ctypes.c_int]
         L.b2r_emu_set_cols_staged.argtypes = [ctypes.c_int]
+        L.b2r_emu_set_cols_2x.argtypes = [ctypes.c_int]
         L.b2r_emu_set_sharpen_fast.argtypes = [ctypes.c_int]
         L.b2r_emu_u8_to_planar.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
         L.b2r_emu_planar_to_u8.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]

@@ -384,3 +384,28 @@ def test_cols_staged_kernel_equals_direct_kernel(w, h):
         L.b2r_emu_set_cols_staged(0)
     assert a["used_static"] & 2 and b["used_static"] & 2
     assert np.array_equal(a["spec2"].view(np.uint64), b["spec2"].view(np.uint64))
+
+
+@pytest.mark.parametrize("w,h,prec", [(256, 128, 0), (24, 512, 0), (60, 360, 2), (32, 1024, 0)])
+def test_cols_exact_2x_kernel(w, h, prec):
+    """the exact-2x column kernel (even output rows = the input rows / 2, odd rows = an H-point inverse of the
+    forward spectrum times the half-sample phase ramp, Nyquist row on the negative side) against the generic
+    kernel (forward H, shift / zero-pad remap, inverse 2H) and against the float64 oracle"""
+    plan = vo.make_plan(w, h, 2.0)
+    x = vo.synthetic_frame("noise", w, h, 21)
+    L = eu.lib()
+    a = eu.frame(x, 2.0, prec, 0.2, plan)
+    L.b2r_emu_set_cols_2x(1)
+    try:
+        b = eu.frame(x, 2.0, prec, 0.2, plan)
+    finally:
+        L.b2r_emu_set_cols_2x(0)
+    assert a["used_static"] & 2 and b["used_static"] & 2
+    mag = np.abs(a["spec2"]).max()
+    assert np.abs(a["spec2"] - b["spec2"]).max() <= 2e-6 * mag
+    # even rows are exactly the scaled input rows
+    assert np.array_equal(b["spec2"][:, 0::2, :], (b["spec1"] * np.float32(0.5)).astype(np.complex64))
+    xin = x.astype(np.float16 if prec == 2 else np.float32)
+    pre_o = vo.pre_sharpen(xin, plan, precision=prec, dtype=np.float64)
+    tol = 1e-5 if prec == 0 else 2e-3
+    assert np.abs(b["pre"].astype(np.float64) - pre_o.astype(np.float64)).max() * plan.up2 <= tol

@@ -13,6 +13,7 @@
 // events on the plan's stream.
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -124,6 +125,7 @@ struct b2r_plan {
     int kernels_per_frame = 4;
     unsigned char* u8_in0 = nullptr;   // lane 0's u8 staging
     unsigned char* u8_out0 = nullptr;
+    float2* d_ramp = nullptr;  // exact-2x column kernel: half-sample phase ramp (H entries); nullptr = k_cols
     // fused C2R + sharpen (b2r_fused.cuh): strips per plane, fix-up list (device), 0 = separate kernels
     int fused_nsp = 0;
     int* d_fix = nullptr;
@@ -173,7 +175,12 @@ int launch_frame(b2r_plan* p, cudaStream_t s, const void* d_in = nullptr, void* 
     CU(p->k_r2c.r2c(s, a1, p->k_r2c.sched.threads, p->k_r2c.smem, p->k_r2c.ctx));
     if (ev) CU(cudaEventRecord(ev[1], s));
     ColsArgs a2{spec1, spec2, p->tw_h, p->tw_uh, p->d_fd + 1, p->d_fd + 2, p->dm, 1.0f / (float)g.up_h, nyq};
-    CU(p->k_cols.launch(s, a2, p->k_cols.inv.threads, p->k_cols.smem, p->k_cols.ctx));
+    if (p->d_ramp) {   // upH == 2H: even rows copied, odd rows by an H-point inverse (k_cols2x)
+        a2.ramp = p->d_ramp;
+        CU(p->k_cols.launch2x(s, a2, p->k_cols.fwd.threads, p->k_cols.smem2x, p->k_cols.ctx));
+    } else {
+        CU(p->k_cols.launch(s, a2, p->k_cols.inv.threads, p->k_cols.smem, p->k_cols.ctx));
+    }
     if (ev) CU(cudaEventRecord(ev[2], s));
     if (p->fused_nsp > 0) {   // K7 + K8 in one kernel; the boundary rows go through the pre-sharpen buffer
         FusedArgs af{spec2, d_out ? d_out : (ln ? ln->d_out : p->d_out), pre, p->tw_uw, p->dm, g.precision,
@@ -446,6 +453,19 @@ int build(b2r_plan* p) {
         (rc = put(p->fuw, &p->tw_uw)))
         return rc;
 
+    // exact-2x column kernel: built-in schedule pairs with upH == 2H, single precision (B2R_COLS_2X=0 keeps k_cols)
+    if (p->k_cols.launch2x) {   // (set by the static registry only: upH == 2H, single precision, B2R_COLS_2X != 0)
+        if (p->k_cols.smem2x > smem_max) return fail(B2R_ERR_UNSUPPORTED, "column tile does not fit one CTA");
+        CU(p->k_cols.prepare2x(p->k_cols.smem2x, p->k_cols.ctx));
+        std::vector<float2> ramp((size_t)g.h);
+        for (int k = 0; k < g.h; ++k) {
+            const int ks = (k < g.h / 2) ? k : k - g.h;       // signed frequency after the reference's shift
+            const double a = 3.14159265358979323846 * (double)ks / (double)g.h;
+            ramp[(size_t)k] = make_float2((float)std::cos(a), (float)std::sin(a));
+        }
+        CU(cudaMalloc((void**)&p->d_ramp, ramp.size() * sizeof(float2)));
+        CU(cudaMemcpy(p->d_ramp, ramp.data(), ramp.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    }
     if (p->fused_nsp > 0) {   // rows k_sharpen_fix finishes, per plane (b2r_fused.cuh)
         std::vector<int> fix;
         const int ppp = g.up_h / 2, nsp = p->fused_nsp;
@@ -477,7 +497,7 @@ int build(b2r_plan* p) {
 extern "C" {
 
 const char* b2r_last_error(void) { return g_err.c_str(); }
-const char* b2r_version(void) { return "b2resample 0.1 (sm_100a)"; }
+const char* b2r_version(void) { return "b2resample 0.2 (sm_100a)"; }
 
 int b2r_device_count(void) {
     int n = 0;
@@ -543,7 +563,7 @@ void b2r_plan_destroy(b2r_plan* p) {
     if (p->stream) cudaStreamDestroy(p->stream);
     cudaFree(p->d_in); cudaFree(p->d_pre); cudaFree(p->d_out);
     cudaFree(p->d_spec1); cudaFree(p->d_spec2); cudaFree(p->d_tw); cudaFree(p->d_fd); cudaFree(p->d_nyq);
-    cudaFree(p->d_fix);
+    cudaFree(p->d_fix); cudaFree(p->d_ramp);
     delete p;
 }
 

@@ -20,6 +20,7 @@ struct R2cArgs {
 struct ColsArgs {
     const float2* in; float2* out; const float2 *tw_f, *tw_i; const FftDesc *dfd_f, *dfd_i; FrameDims dm; float scale;
     float2* nyq = nullptr;   // C2C parity mode: receives F[H/2][x] of the forward column transform
+    const float2* ramp = nullptr;   // exact-2x column kernel: half-sample phase ramp, H entries (nullptr: k_cols)
 };
 struct C2rArgs {
     const float2* spec; void* pre; const float2* tw; const FftDesc* dfd; FrameDims dm; int precision; float scale;
@@ -76,6 +77,10 @@ struct ColImpl {       // fused column kernel resolved for one (H, upH) pair
     bool is_jit = false;
     cudaError_t (*prepare)(size_t smem, const void* ctx) = nullptr;
     cudaError_t (*launch)(cudaStream_t, const ColsArgs&, int threads, size_t smem, const void* ctx) = nullptr;
+    // exact-2x form (k_cols2x): two H-point transforms, even rows copied; nullptr when not instantiated
+    size_t smem2x = 0;
+    cudaError_t (*prepare2x)(size_t smem, const void* ctx) = nullptr;
+    cudaError_t (*launch2x)(cudaStream_t, const ColsArgs&, int threads, size_t smem, const void* ctx) = nullptr;
 };
 
 // static registries: return false when the size was not instantiated at build time

@@ -7,6 +7,7 @@
 
 namespace b2r {
 namespace {
+template <class P> void sched_of_fwd(Schedule* sc);
 template <class PF, class PI, int CC> cudaError_t prep(size_t smem, const void*) {
     if (smem <= 48 * 1024) return cudaSuccess;
     return cudaFuncSetAttribute(k_cols<PF, PI, CC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -38,6 +39,25 @@ template <class PF, class PI, int CC> cudaError_t run_staged(cudaStream_t s, con
     return cudaGetLastError();
 }
 
+// ---- exact-2x column kernel (k_cols2x): default for the 2x pairs; B2R_COLS_2X=0 keeps k_cols
+template <class PF, int CC, int MINB = 0> cudaError_t prep2x(size_t smem, const void*) {
+    if (smem <= 48 * 1024) return cudaSuccess;
+    return cudaFuncSetAttribute(k_cols2x<PF, CC, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+}
+template <class PF, int CC, int MINB = 0> cudaError_t run2x(cudaStream_t s, const ColsArgs& a, int, size_t smem, const void*) {
+    dim3 block(PF::kT * CC), grid((a.dm.nx + CC - 1) / CC, 3);
+    k_cols2x<PF, CC, MINB><<<grid, block, smem, s>>>(a.in, a.out, a.tw_f, a.ramp, PF{}, a.dm, a.scale, a.nyq);
+    return cudaGetLastError();
+}
+// tuning variants of the exact-2x kernel (B2R_COLS_2X_VARIANT=1..): other thread counts / tile widths / register targets
+template <class PF, int CC, int MINB> void use2x(ColImpl* o) {
+    o->cc = CC;
+    sched_of_fwd<PF>(&o->fwd);
+    o->smem2x = (size_t)smem_padded_len(PF::kN * CC) * sizeof(float2);
+    o->prepare2x = &prep2x<PF, CC, MINB>;
+    o->launch2x = &run2x<PF, CC, MINB>;
+}
+
 template <class PF, class PI, int CC> constexpr bool grouped_ok() {
     return PI::kT % 32 == 0 && PF::kStages >= 2 && PI::kStages >= 3 && CC <= 15;
 }
@@ -58,6 +78,10 @@ template <class PF, class PI, int CC> cudaError_t run_grouped(cudaStream_t s, co
         return cudaErrorInvalidValue;
     }
 }
+template <class P> void sched_of_fwd(Schedule* sc) {
+    sc->n = P::kN; sc->nst = P::kStages; sc->threads = P::kT;
+    for (int s = 0; s < P::kStages; ++s) sc->radices[s] = P::radix(s);
+}
 template <class P> void sched_of(Schedule* sc) {
     sc->n = P::kN; sc->nst = P::kStages; sc->threads = P::kT;
     for (int s = 0; s < P::kStages; ++s) sc->radices[s] = P::radix(s);
@@ -70,10 +94,37 @@ template <class PF, class PI, int CC> void fill(ColImpl* o, const char* name) {
     o->smem = (size_t)smem_padded_len(PI::kN * CC) * sizeof(float2);
     o->prepare = &prep<PF, PI, CC>;
     o->launch = &run<PF, PI, CC>;
-    // Named-barrier variant (one thread group per column), opt-in with B2R_COLS_GROUPED=1.  Measured on
-    // B200 it is NOT faster than the CTA-barrier kernel (c2: 42.7 vs 41.4 us; c5: 335 vs 321 us): the
-    // barrier stalls ncu attributes to k_cols are warps waiting for shared-memory traffic of their
-    // peers, which a narrower barrier does not remove.  Kept for that record and for the tests.
+    if constexpr (PI::kN == 2 * PF::kN) {
+        // exact-2x pairs run k_cols2x unless B2R_COLS_2X=0.  Decided HERE because the tuned 2x variants may use another
+        // H-point schedule than the generic kernel's forward transform: o->fwd (from which the plan builds the
+        // twiddle table) and o->cc must describe the kernel that actually runs.  Tuned on B200 (profiles/README.md):
+        // 1024: 64 threads per column x 8 columns (28.7 us against 35.0 for 128 x 4); 2160: 144 x 4 with a
+        // two-CTA register target (116 against 133 us); 1080: 90 x 8.
+        const char* e2 = getenv("B2R_COLS_2X");
+        if (!(e2 && atoi(e2) == 0)) {
+            const char* ev = getenv("B2R_COLS_2X_VARIANT");
+            const int var = ev ? atoi(ev) : 0;
+            use2x<PF, CC, 0>(o);
+            if constexpr (PF::kN == 1024) {
+                use2x<ColF1024h, 8, 0>(o);
+                if (var == 1) use2x<ColF1024h, 4, 0>(o);        // 64 threads per column, 256-thread CTAs
+                if (var == 2) use2x<ColF1024, 4, 0>(o);         // the generic kernel's shape
+                if (var == 3) use2x<ColF1024, 8, 0>(o);         // 8-column tiles, 1024 threads
+            }
+            if constexpr (PF::kN == 2160) {
+                use2x<ColF2160, 4, 2>(o);
+                if (var == 1) use2x<ColF2160, 4, 0>(o);         // one resident CTA (86 registers)
+            }
+            if constexpr (PF::kN == 1080) {
+                if (var == 1) use2x<ColF1080, 4, 0>(o);         // 360-thread CTAs
+                if (var == 2) use2x<ColF1080n, 4, 0>(o);
+            }
+            if constexpr (PF::kN == 512) {
+                if (var == 1) use2x<StaticFft<512, 32, 16, 8, 4>, 8, 0>(o);
+            }
+            return;
+        }
+    }
     const char* es = getenv("B2R_COLS_STAGED");
     if (es && atoi(es) != 0 && cols_staged_smem_bytes(PF::kN, PI::kN, CC, sizeof(float2)) <= 227 * 1024) {
         o->name = "cols_staged";
