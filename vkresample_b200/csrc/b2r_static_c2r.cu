@@ -40,6 +40,36 @@ template <class P> cudaError_t prep_bulk(size_t, const void*) {
     if ((e = cudaFuncSetAttribute(k_c2r_rows_bulk<P, __half, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, n))) return e;
     return cudaFuncSetAttribute(k_c2r_rows_bulk<P, __half, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, n);
 }
+// single staging buffer (refilled after the first stage): B2R_C2R_BULK=2; measured in profiles/README.md
+template <class P, class TOut, bool UP2> cudaError_t run_bulk1_t(cudaStream_t s, const C2rArgs& a) {
+    const int pairs = 3 * a.dm.up_h / 2;
+    const size_t smem = c2r_bulk1_smem_bytes(P::kN, a.dm.nx);
+    static thread_local int dev_cached = -1, sms = 0;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev != dev_cached) { cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); dev_cached = dev; }
+    int per_sm = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_c2r_rows_bulk<P, TOut, UP2, true>, P::kT, smem);
+    if (e != cudaSuccess) return e;
+    int grid = sms * (per_sm > 0 ? per_sm : 1);
+    if (grid > pairs) grid = pairs;
+    k_c2r_rows_bulk<P, TOut, UP2, true><<<grid, P::kT, smem, s>>>(a.spec, (TOut*)a.pre, a.tw, P{}, a.dm, pairs, a.scale);
+    return cudaGetLastError();
+}
+template <class P, int PPB> cudaError_t run_bulk1(cudaStream_t s, const C2rArgs& a, int, size_t, const void*) {
+    const bool up2 = (a.dm.up_w == 2 * a.dm.w);
+    if (a.precision == 2) return up2 ? run_bulk1_t<P, __half, true>(s, a) : run_bulk1_t<P, __half, false>(s, a);
+    return up2 ? run_bulk1_t<P, float, true>(s, a) : run_bulk1_t<P, float, false>(s, a);
+}
+template <class P> cudaError_t prep_bulk1(size_t, const void*) {
+    const int n = (int)(16 + 2 * 4100 * sizeof(float2) + smem_padded_len(P::kN) * sizeof(float2));
+    cudaError_t e;
+    if ((e = cudaFuncSetAttribute(k_c2r_rows_bulk<P, float, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, n))) return e;
+    if ((e = cudaFuncSetAttribute(k_c2r_rows_bulk<P, float, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, n))) return e;
+    if ((e = cudaFuncSetAttribute(k_c2r_rows_bulk<P, __half, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, n))) return e;
+    return cudaFuncSetAttribute(k_c2r_rows_bulk<P, __half, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, n);
+}
+
 template <class P, class TOut, bool UP2> cudaError_t run_bulk_t(cudaStream_t s, const C2rArgs& a) {
     const int pairs = 3 * a.dm.up_h / 2;
     const size_t smem = c2r_bulk_smem_bytes(P::kN, a.dm.nx);
@@ -142,6 +172,11 @@ template <class P, int PPB> void fill(RowImpl* o, const char* name) {
         o->ppb = 1;
         o->prepare = &prep_bulk<P>;
         o->c2r = &run_bulk<P, PPB>;
+        if (e && atoi(e) == 2) {
+            o->name = "c2r_rows_bulk1";
+            o->prepare = &prep_bulk1<P>;
+            o->c2r = &run_bulk1<P, PPB>;
+        }
     }
 }
 }  // namespace
