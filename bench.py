@@ -484,7 +484,7 @@ def main():
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--frames-per-step", type=int, default=0,
                     help="frames per step per GPU; 0 (default): calibrated so that the timed region lasts >= --min-seconds")
-    ap.add_argument("--min-seconds", type=float, default=2.5, help="length of the device-resident timed region")
+    ap.add_argument("--min-seconds", type=float, default=2.8, help="length of the device-resident timed region")
     ap.add_argument("--min-seconds-e2e", type=float, default=1.2, help="length of each host-fed timed region")
     ap.add_argument("--no-affinity", action="store_true", help="N > 1: do not bind ranks to their GPU's NUMA-local CPUs")
     ap.add_argument("--ring", type=int, default=8)
