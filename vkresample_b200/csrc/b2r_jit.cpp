@@ -249,7 +249,8 @@ bool jit_build(const JitRequest& rq, JitModule** out_mod, RowImpl* r2c, ColImpl*
     Api& a = api();
     if (!a.ok) { *err = a.why; return false; }
     const std::string csrc = this_library_dir() + "/../csrc";
-    const std::string hdr = slurp(csrc + "/b2r_kernels.cuh") + slurp(csrc + "/b2r_fft.cuh") + slurp(csrc + "/b2r_common.cuh") + slurp(csrc + "/b2r_cas.cuh");
+    const std::string hdr = slurp(csrc + "/b2r_kernels.cuh") + slurp(csrc + "/b2r_fft.cuh") + slurp(csrc + "/b2r_common.cuh") + slurp(csrc + "/b2r_cas.cuh") +
+                            slurp(csrc + "/b2r_fused.cuh");
     if (hdr.empty()) { *err = "kernel headers not found next to the library (" + csrc + ")"; return false; }
 
     // ---- source: explicit instantiations of exactly the kernels this plan launches
