@@ -386,7 +386,7 @@ def test_cols_staged_kernel_equals_direct_kernel(w, h):
     assert np.array_equal(a["spec2"].view(np.uint64), b["spec2"].view(np.uint64))
 
 
-@pytest.mark.parametrize("w,h,prec", [(256, 128, 0), (24, 512, 0), (60, 360, 2), (32, 1024, 0)])
+@pytest.mark.parametrize("w,h,prec", [(256, 128, 0), (24, 512, 0), (60, 360, 2), (32, 1024, 0), (16, 1080, 0), (16, 540, 0)])
 def test_cols_exact_2x_kernel(w, h, prec):
     """the exact-2x column kernel (even output rows = the input rows / 2, odd rows = an H-point inverse of the
     forward spectrum times the half-sample phase ramp, Nyquist row on the negative side) against the generic

@@ -226,6 +226,13 @@ template <int R> B2R_DEV void apply_twiddle_powers(real2 (&v)[R], real2 w) {
 // and the contiguous reads of all stages free of bank conflicts for power-of-two radices.
 B2R_HD int smem_pad(int i) { return i + (i >> 4); }
 B2R_HD constexpr int smem_padded_len(int n) { return n + (n >> 4) + 1; }
+// Layout policy of a kernel: PAD = false addresses the workspace linearly.  Schedules whose first radix is odd
+// want that in the column kernels: with CS columns side by side a half-warp touches 16/CS runs of CS consecutive
+// elements whose distance (in sequence elements) is 1 for every read and every later-stage write and R0 for the
+// first-stage writes -- odd distances spread the runs over the sixteen 8-byte bank pairs by themselves, and the
+// extra element after every 16 then only misaligns them (scripts/smem_conflicts.py: 1080 = 15.12.6 x 8 columns,
+// 23.5 % of the wavefronts are conflict replays with the padding, 1.3 % without).
+template <bool PAD> B2R_HD int smem_at(int i) { return PAD ? i + (i >> 4) : i; }
 
 // exact j / d for j < 2^16 via one mul.hi (magic = ceil(2^32 / d)), d >= 2
 struct FastDiv {
@@ -301,7 +308,7 @@ template <int R_, int NB_> struct DynStage {
 // cs = columns per CTA for the column kernel, so that the batch index is the fastest dimension).
 
 // shared -> registers, outer twiddle w = exp(DIR*2*pi*i*p/(S*R)) (one table load), butterfly
-template <int DIR, int CS, class St>
+template <int DIR, int CS, bool PAD = true, class St>
 B2R_DEV void stage_load_compute(const St st, const real2* sm, const real2* __restrict__ tw, int T, int tid,
                                 int c, real2 (&v)[St::NB][St::R]) {
     constexpr int R = St::R;
@@ -309,7 +316,11 @@ B2R_DEV void stage_load_compute(const St st, const real2* sm, const real2* __res
     for (int b = 0; b < St::NB; ++b) {
         int j = tid + b * T;
         if (j < st.nb()) {
-            if constexpr (St::template read_const<CS>()) {
+            if constexpr (!PAD) {
+                const real2* base = sm + (j * CS + c);
+#pragma unroll
+                for (int i = 0; i < R; ++i) v[b][i] = base[i * st.nb() * CS];
+            } else if constexpr (St::template read_const<CS>()) {
                 const real2* base = sm + smem_pad(j * CS + c);
                 const int step = st.nb() * CS + ((st.nb() * CS) >> 4);
 #pragma unroll
@@ -341,7 +352,7 @@ B2R_DEV void stage_compute_first(const St st, int T, int tid, real2 (&v)[St::NB]
 }
 
 // registers -> shared at the Stockham output index  p + (j div S)*S*R + k*S
-template <int CS, class St>
+template <int CS, bool PAD = true, class St>
 B2R_DEV void stage_store(const St st, real2* sm, int T, int tid, int c, real2 (&v)[St::NB][St::R]) {
     constexpr int R = St::R;
 #pragma unroll
@@ -351,7 +362,13 @@ B2R_DEV void stage_store(const St st, real2* sm, int T, int tid, int c, real2 (&
             int q, p;
             st.split(j, q, p);
             int base = q * st.stride() * R + p;
-            if constexpr (St::template write_const<CS>()) {
+            if constexpr (!PAD) {
+                real2* dst = sm + (base * CS + c);
+                static_for<0, R>([&](auto k) {
+                    constexpr int K = decltype(k)::value;
+                    dst[K * st.stride() * CS] = v[b][dft_slot<R>(K)];
+                });
+            } else if constexpr (St::template write_const<CS>()) {
                 real2* dst = sm + smem_pad(base * CS + c);
                 static_for<0, R>([&](auto k) {
                     constexpr int K = decltype(k)::value;
