@@ -92,6 +92,7 @@ static FrameDims dims_of(const Geometry& g) {
     d.zp_lo = g.zp_lo; d.zp_hi = g.zp_hi; d.neg_shift = g.neg_shift;
     d.in_plane = g.in_plane; d.pre_plane = g.pre_plane; d.out_plane = g.out_plane;
     d.up2 = g.up2; d.sharpen = g.sharpen;
+    { const CasK k = cas_k(d.sharpen); d.cas_a = k.a; d.cas_b = k.b; }
     return d;
 }
 

@@ -384,6 +384,7 @@ int build(b2r_plan* p) {
     const bool raw = p->flags & B2R_FLAG_NO_SHARPEN_LITERAL_ROUNDING;
     d.up2 = raw ? g.up2 : literal_f(g.up2);
     d.sharpen = raw ? g.sharpen : literal_f(g.sharpen);
+    { const CasK k = cas_k(d.sharpen); d.cas_a = k.a; d.cas_b = k.b; }
     d.up2_d = raw ? (double)g.up2 : literal_d(g.up2);
     d.sharpen_d = raw ? (double)g.sharpen : literal_d(g.sharpen);
 

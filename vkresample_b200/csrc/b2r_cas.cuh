@@ -11,8 +11,10 @@
 //     With sA = mn0+mn1 and u = 2-(mx0+mx1):  a = f(sA), b = f(u), f(z) = z/(2-z) increasing on [0,2),
 //     so min(a, b) = f(min(sA, u)) -- one quotient instead of two, and since mn <= mx gives
 //     sA + u <= 2 the selected m = min(sA, u) is <= 1: the divisor 2-m lies in [1, 2] (no special cases).
-//   * sqrt(m/(2-m)) = m * rsqrt(m*(2-m) + 1e-30): one MUFU instead of two; the 1e-30 (folded into the
+//   * -s*sqrt(m/(2-m)) = -m * rsqrt(m*(2-m)/s^2 + 1e-30): one MUFU instead of two, and the sharpen constant
+//     rides in the FFMA that forms 2-m ((2-m)/s^2 = m*(-1/s^2) + 2/s^2, CasK); the 1e-30 (folded into the
 //     FFMA that forms the product) makes m = 0 give exactly 0 instead of 0*inf.
+//   * the tap clamp min(|up2*x|, 1) is the saturating multiply up2*|x| (one FMUL.SAT / HMUL2.SAT).
 //   * the final quotient is num * rcp(den); den = 1 + 4*scale*(-s) stays in [0.04, 1] for 0 <= s <= 0.24
 //     (other constants keep the exact kernel).
 //   * vertical 3-min / 3-max per column are shared by the three pixels that use the column; every
@@ -43,14 +45,29 @@ B2R_DEV float cas_rcp(float x) { return 1.0f / x; }
 B2R_DEV float cas_rsqrt(float x) { return 1.0f / sqrtf(x); }
 #endif
 
-// clamped magnitude of one tap: min(|up2 * x|, 1)   (VkResample.cpp:893-907; the < 0 clamp cannot fire)
-B2R_DEV float cas_tap(float up2, float x) { return fminf(fabsf(up2 * x), 1.0f); }
+// clamped magnitude of one tap: min(|up2 * x|, 1)   (VkResample.cpp:893-907; the < 0 clamp cannot fire):
+// up2 > 0, so |up2 * x| = up2 * |x| exactly and the clamp is the multiply's saturation modifier
+#if defined(__CUDA_ARCH__)
+B2R_DEV float cas_tap(float up2, float x) { return __saturatef(up2 * fabsf(x)); }
+#else
+B2R_DEV float cas_tap(float up2, float x) { return fminf(fmaxf(up2 * fabsf(x), 0.0f), 1.0f); }
+#endif
+
+// sharpen constant folded for the rsqrt argument: (2 - m) / s^2 = fma(m, a, b).  s = 0 takes 1/s^2 = 1e30:
+// the scale then comes out as -1e-15 * sqrt(m/(2-m)), i.e. the pixel passes through to 1e-15.
+// Evaluated once per plan on the host (FrameDims::cas_a / cas_b).
+struct CasK { float a, b; };
+inline CasK cas_k(float sharpen) {
+    const float inv = (sharpen != 0.0f) ? 1.0f / (sharpen * sharpen) : 1e30f;
+    CasK k; k.a = -inv; k.b = 2.0f * inv;
+    return k;
+}
 
 // One output row segment.  up / mid / dn: clamped magnitudes of columns x0-1 .. x0+NP of rows y-1, y, y+1;
-// o[i]: sharpened pixel x0+i.  neg_s = -sharpen.
+// o[i]: sharpened pixel x0+i.  ks = cas_k(sharpen).
 template <int NP>
 B2R_DEV void cas_row_f32(const float (&up)[NP + 2], const float (&mid)[NP + 2], const float (&dn)[NP + 2],
-                         const float neg_s, float (&o)[NP]) {
+                         const CasK ks, float (&o)[NP]) {
     float vmn[NP + 2], vmx[NP + 2];
 #pragma unroll
     for (int c = 0; c < NP + 2; ++c) {
@@ -66,9 +83,7 @@ B2R_DEV void cas_row_f32(const float (&up)[NP + 2], const float (&mid)[NP + 2], 
         const float sA = mn0 + mn1;
         const float u = 2.0f - (mx0 + mx1);
         const float m = fminf(sA, u);
-        const float d = 2.0f - m;
-        const float g = m * cas_rsqrt(fmaf(m, d, 1e-30f));
-        const float sc = neg_s * g;
+        const float sc = -m * cas_rsqrt(fmaf(m, fmaf(m, ks.a, ks.b), 1e-30f));   // -s * sqrt(m / (2 - m))
         const float cross = (up[i + 1] + dn[i + 1]) + (mid[i] + mid[i + 2]);
         o[i] = fmaf(sc, cross, mid[i + 1]) * cas_rcp(fmaf(sc, 4.0f, 1.0f));
     }
@@ -99,10 +114,14 @@ B2R_DEV __half2 cas_hfma2(__half2 a, __half2 b, __half2 c) {   // exact product 
     return __halves2half2(__double2half((double)x.x * y.x + z.x), __double2half((double)x.y * y.y + z.y));
 }
 #endif
+#if defined(__CUDA_ARCH__)
+B2R_DEV __half2 cas_tap2(__half2 up2, __half2 x) { return __hmul2_sat(up2, __habs2(x)); }
+#else
 B2R_DEV __half2 cas_tap2(__half2 up2, __half2 x) {
     const __half2 one = __float2half2_rn(1.0f);
-    return h2min3(__habs2(__hmul2(up2, x)), one, one);   // (2-input min: FMNMX3-style duplicate operand)
+    return h2min3(__habs2(__hmul2(up2, x)), one, one);
 }
+#endif
 
 // a[k] = columns (x0-1+2k, x0+2k), k = 0 .. NP/2     (pairs starting at the odd column x0-1; a[NP/2] ends at x0+NP)
 // b[k] = columns (x0+2k, x0+2k+1),   k = 0 .. NP/2-1   (the thread's own aligned pairs)
@@ -119,7 +138,7 @@ template <int NP> struct CasRowH {
 
 // o[k] = sharpened pixels (x0+2k, x0+2k+1)
 template <int NP>
-B2R_DEV void cas_row_f16(const CasRowH<NP>& up, const CasRowH<NP>& mid, const CasRowH<NP>& dn, const __half2 neg_s,
+B2R_DEV void cas_row_f16(const CasRowH<NP>& up, const CasRowH<NP>& mid, const CasRowH<NP>& dn, const CasK ks,
                          __half2 (&o)[NP / 2]) {
     constexpr int H = NP / 2;
     __half2 vna[H + 1], vxa[H + 1], vnb[H], vxb[H];
@@ -127,7 +146,7 @@ B2R_DEV void cas_row_f16(const CasRowH<NP>& up, const CasRowH<NP>& mid, const Ca
     for (int k = 0; k <= H; ++k) { vna[k] = h2min3(up.a[k], mid.a[k], dn.a[k]); vxa[k] = h2max3(up.a[k], mid.a[k], dn.a[k]); }
 #pragma unroll
     for (int k = 0; k < H; ++k) { vnb[k] = h2min3(up.b[k], mid.b[k], dn.b[k]); vxb[k] = h2max3(up.b[k], mid.b[k], dn.b[k]); }
-    const __half2 two = __float2half2_rn(2.0f), four = __float2half2_rn(4.0f), one = __float2half2_rn(1.0f);
+    const __half2 two = __float2half2_rn(2.0f);
 #pragma unroll
     for (int k = 0; k < H; ++k) {
         // pixel pair (x0+2k, x0+2k+1): centre = b[k]; left = a[k]; right = a[k+1]
@@ -138,14 +157,15 @@ B2R_DEV void cas_row_f16(const CasRowH<NP>& up, const CasRowH<NP>& mid, const Ca
         const __half2 sA = __hadd2(mn0, mn1);
         const __half2 u = __hsub2(two, __hadd2(mx0, mx1));
         const __half2 m = __hmin2(sA, u);
-        const __half2 d = __hsub2(two, m);
-        // g = sqrt(m/d) in float on the half operands
-        const float2 mf = __half22float2(m), df = __half22float2(d);
-        const __half2 g = __floats2half2_rn(mf.x * cas_rsqrt(fmaf(mf.x, df.x, 1e-30f)), mf.y * cas_rsqrt(fmaf(mf.y, df.y, 1e-30f)));
-        const __half2 sc = __hmul2(neg_s, g);
+        // the two MUFU steps in float on the half operand: scale = -s*sqrt(m/(2-m)) as in cas_row_f32, its
+        // half rounding feeds the numerator, the float value the reciprocal of the denominator
+        const float2 mf = __half22float2(m);
+        const float sx = -mf.x * cas_rsqrt(fmaf(mf.x, fmaf(mf.x, ks.a, ks.b), 1e-30f));
+        const float sy = -mf.y * cas_rsqrt(fmaf(mf.y, fmaf(mf.y, ks.a, ks.b), 1e-30f));
+        const __half2 sc = __floats2half2_rn(sx, sy);
         const __half2 cross = __hadd2(__hadd2(up.b[k], dn.b[k]), __hadd2(mid.a[k], mid.a[k + 1]));
-        const float2 num = __half22float2(cas_hfma2(sc, cross, mid.b[k])), den = __half22float2(cas_hfma2(sc, four, one));
-        o[k] = __floats2half2_rn(num.x * cas_rcp(den.x), num.y * cas_rcp(den.y));
+        const __half2 num = cas_hfma2(sc, cross, mid.b[k]);
+        o[k] = __hmul2(num, __floats2half2_rn(cas_rcp(fmaf(sx, 4.0f, 1.0f)), cas_rcp(fmaf(sy, 4.0f, 1.0f))));
     }
 }
 
@@ -178,7 +198,8 @@ k_sharpen_fast_f32(const float* __restrict__ pre, float* __restrict__ out, const
     int by = (int)B2R_BID_Y, ch = (int)B2R_BID_Z;
     if (reverse) { by = (int)B2R_GDIM_Y - 1 - by; ch = (int)B2R_GDIM_Z - 1 - ch; }
     const int y_begin = by * ry;
-    const float up2 = dm.up2, neg_s = -dm.sharpen;
+    const float up2 = dm.up2;
+    const CasK ks = {dm.cas_a, dm.cas_b};
     const float* plane = pre + (size_t)ch * dm.pre_plane;
     float* oplane = out + (size_t)ch * dm.out_plane;
     const bool in_row = x0 < dm.up_w;            // lanes past the row end only take part in the shuffles
@@ -235,7 +256,7 @@ k_sharpen_fast_f32(const float* __restrict__ pre, float* __restrict__ out, const
         finish_row(q, dn);                                   // row y+1
         if (more && y + 2 < dm.up_h) fetch_row(y + 3, q);    // needed by output row y+2
         float o[NP];
-        cas_row_f32<NP>(up, mid, dn, neg_s, o);
+        cas_row_f32<NP>(up, mid, dn, ks, o);
         if (in_row) {
             float* dst = oplane + (size_t)y * dm.up_w + x0;
 #pragma unroll
@@ -269,15 +290,16 @@ k_sharpen_fast_f32(const float* __restrict__ pre, float* __restrict__ out, const
 }
 
 // fp16: one thread = 8 pixels (one 16-byte vector) per row
-template <int NP>
-B2R_KERNEL B2R_LAUNCH_BOUNDS(256, 3)
+template <int NP, int MINB = 3>
+B2R_KERNEL B2R_LAUNCH_BOUNDS(256, MINB)
 k_sharpen_fast_f16(const __half* __restrict__ pre, __half* __restrict__ out, const FrameDims dm, const int ry, const int reverse) {
     static_assert(NP == 8, "one 16-byte vector per thread and row");
     const int x0 = (int)(B2R_BID_X * B2R_BDIM_X + B2R_TID_X) * NP;
     int by = (int)B2R_BID_Y, ch = (int)B2R_BID_Z;
     if (reverse) { by = (int)B2R_GDIM_Y - 1 - by; ch = (int)B2R_GDIM_Z - 1 - ch; }
     const int y_begin = by * ry;
-    const __half2 up2 = __float2half2_rn(dm.up2), neg_s = __float2half2_rn(-dm.sharpen);
+    const __half2 up2 = __float2half2_rn(dm.up2);
+    const CasK ks = {dm.cas_a, dm.cas_b};
     const __half* plane = pre + (size_t)ch * dm.pre_plane;
     __half* oplane = out + (size_t)ch * dm.out_plane;
     const bool in_row = x0 < dm.up_w;
@@ -328,7 +350,7 @@ k_sharpen_fast_f16(const __half* __restrict__ pre, __half* __restrict__ out, con
         finish_row(q, dn);
         if (more && y + 2 < dm.up_h) fetch_row(y + 3, q);
         __half2 o[NP / 2];
-        cas_row_f16<NP>(up, mid, dn, neg_s, o);
+        cas_row_f16<NP>(up, mid, dn, ks, o);
         if (in_row) {
             const uint4 v = make_uint4(as_u32(o[0]), as_u32(o[1]), as_u32(o[2]), as_u32(o[3]));
             uint4* dst = reinterpret_cast<uint4*>(oplane + (size_t)y * dm.up_w + x0);

@@ -95,7 +95,8 @@ k_c2r_sharpen_f32(const real2* __restrict__ spec, float* __restrict__ out, float
     real2* const stg = reinterpret_cast<real2*>(smem_base + 16);
     real2* const ws0 = stg + 4 * (size_t)row_elems;
     const int ws_len = fused_ws_len(n);
-    const float up2 = dm.up2, neg_s = -dm.sharpen;
+    const float up2 = dm.up2;
+    const CasK ks = {dm.cas_a, dm.cas_b};
     const real2* sp = spec + (size_t)c * dm.up_h * dm.spec_stride;
     float* oplane = out + (size_t)c * dm.out_plane;
     float* pplane = pre + (size_t)c * dm.pre_plane;
@@ -179,7 +180,7 @@ k_c2r_sharpen_f32(const real2* __restrict__ spec, float* __restrict__ out, float
                     float tc[NP + 2], td[NP + 2], o[NP];
                     fused_taps4<kShfl>(rowc, ld4(rowc, x0), x0, n, rowc[n], tc);   // row 0; after its end comes row 1
                     fused_taps4<kShfl>(rowd, ld4(rowd, x0), x0, n, 0.f, td);       // row 1; its right end (row 2) is not here yet
-                    cas_row_f32<NP>(tc, tc, td, neg_s, o);
+                    cas_row_f32<NP>(tc, tc, td, ks, o);
                     if (valid) store4(oplane + x0, o);
                 }
                 corner_pending = true;
@@ -201,9 +202,9 @@ k_c2r_sharpen_f32(const real2* __restrict__ spec, float* __restrict__ out, float
                 fused_taps4<kShfl>(rowb, vb, x0, n, end_b, tb);
                 fused_taps4<kShfl>(rowc, vc, x0, n, end_c, tc);
                 fused_taps4<kShfl>(rowd, vd, x0, n, 0.f, td);                // row 2j+2 comes with the next pair
-                cas_row_f32<NP>(ta, tb, tc, neg_s, o);
+                cas_row_f32<NP>(ta, tb, tc, ks, o);
                 if (valid) store4(oplane + (size_t)ya * n + x0, o);
-                cas_row_f32<NP>(tb, tc, td, neg_s, o);
+                cas_row_f32<NP>(tb, tc, td, ks, o);
                 if (valid) store4(oplane + (size_t)yb * n + x0, o);          // its last pixel is redone one pair later
                 va = na; vb = nb; vc = nc; vd = nd;
             }
@@ -215,7 +216,7 @@ k_c2r_sharpen_f32(const real2* __restrict__ spec, float* __restrict__ out, float
                     float mid3[3] = {rowa[n - 2], rowa[n - 1], rowa[n]};
                     float dn3[3] = {rowb[n - 2], rowb[n - 1], rowc[0]};
                     float o1[1];
-                    cas_row_f32<1>(up3, mid3, dn3, neg_s, o1);
+                    cas_row_f32<1>(up3, mid3, dn3, ks, o1);
                     oplane[(size_t)(yb - 2) * n + n - 1] = o1[0];
                 }
                 corner_up0 = rowb[n - 2]; corner_up1 = rowb[n - 1];
@@ -239,7 +240,8 @@ B2R_DEV void sharpen_fix_f32_impl(const float* __restrict__ pre, float* __restri
     if (x0 >= n) return;
     const float* plane = pre + (size_t)ch * dm.pre_plane;
     float* oplane = out + (size_t)ch * dm.out_plane;
-    const float up2 = dm.up2, neg_s = -dm.sharpen;
+    const float up2 = dm.up2;
+    const CasK ks = {dm.cas_a, dm.cas_b};
     const bool plane_end = (b >= dm.up_h);
     // clamped magnitudes of columns x0-1 .. x0+8 of row y (flat +1 on the right, clamp on the left)
     auto taps = [&](int y, float (&t)[NP + 2]) {
@@ -259,11 +261,11 @@ B2R_DEV void sharpen_fix_f32_impl(const float* __restrict__ pre, float* __restri
     taps(b - 2, ta);
     taps(b - 1, tb);
     taps(b, tc);                       // at the plane's end: the zero pad region below the plane
-    cas_row_f32<NP>(ta, tb, tc, neg_s, o);
+    cas_row_f32<NP>(ta, tb, tc, ks, o);
     store8(b - 1, o);
     if (!plane_end) {
         taps(b + 1, td);
-        cas_row_f32<NP>(tb, tc, td, neg_s, o);
+        cas_row_f32<NP>(tb, tc, td, ks, o);
         store8(b, o);
     }
     if (x0 + NP == n) {                // pixel (n-1, b-2): rows b-3 (two elements were stored), b-2, b-1
@@ -272,7 +274,7 @@ B2R_DEV void sharpen_fix_f32_impl(const float* __restrict__ pre, float* __restri
         float mid3[3] = {ta[NP - 1], ta[NP], ta[NP + 1]};
         float dn3[3] = {tb[NP - 1], tb[NP], tb[NP + 1]};
         float o1[1];
-        cas_row_f32<1>(up3, mid3, dn3, neg_s, o1);
+        cas_row_f32<1>(up3, mid3, dn3, ks, o1);
         oplane[(size_t)(b - 2) * n + n - 1] = o1[0];
     }
 }
@@ -339,7 +341,7 @@ k_c2r_sharpen_f16(const real2* __restrict__ spec, __half* __restrict__ out, __ha
     real2* const ws0 = stg + 4 * (size_t)row_elems;
     const int ws_len = fused_ws_len(n);
     const __half up2 = __float2half_rn(dm.up2);
-    const __half2 neg_s = __float2half2_rn(-dm.sharpen);
+    const CasK ks = {dm.cas_a, dm.cas_b};
     const __half hzero = __float2half_rn(0.f);
     const real2* sp = spec + (size_t)c * dm.up_h * dm.spec_stride;
     __half* oplane = out + (size_t)c * dm.out_plane;
@@ -416,7 +418,7 @@ k_c2r_sharpen_f16(const real2* __restrict__ spec, __half* __restrict__ out, __ha
             tm.b[0] = __halves2half2(mid[n - 2], mid[n - 1]); tm.link(mid[n - 3], m_end);
             td.b[0] = __halves2half2(dn[n - 2], dn[n - 1]); td.link(dn[n - 3], d_end);
             __half2 o1[1];
-            cas_row_f16<2>(tu, tm, td, neg_s, o1);
+            cas_row_f16<2>(tu, tm, td, ks, o1);
             oplane[(size_t)y * n + n - 1] = __high2half(o1[0]);
         };
         if (i == 0) {
@@ -429,7 +431,7 @@ k_c2r_sharpen_f16(const real2* __restrict__ spec, __half* __restrict__ out, __ha
                     __half2 o[4];
                     fused_taps8h<kShfl>(rowc, ld8(rowc, x0), x0, n, rowc[n], tc);
                     fused_taps8h<kShfl>(rowd, ld8(rowd, x0), x0, n, hzero, td);
-                    cas_row_f16<NP>(tc, tc, td, neg_s, o);
+                    cas_row_f16<NP>(tc, tc, td, ks, o);
                     if (valid) store8(oplane + x0, o);
                 }
                 corner_pending = true;
@@ -451,9 +453,9 @@ k_c2r_sharpen_f16(const real2* __restrict__ spec, __half* __restrict__ out, __ha
                 fused_taps8h<kShfl>(rowb, vb, x0, n, end_b, tb);
                 fused_taps8h<kShfl>(rowc, vc, x0, n, end_c, tc);
                 fused_taps8h<kShfl>(rowd, vd, x0, n, hzero, td);
-                cas_row_f16<NP>(ta, tb, tc, neg_s, o);
+                cas_row_f16<NP>(ta, tb, tc, ks, o);
                 if (valid) store8(oplane + (size_t)ya * n + x0, o);
-                cas_row_f16<NP>(tb, tc, td, neg_s, o);
+                cas_row_f16<NP>(tb, tc, td, ks, o);
                 if (valid) store8(oplane + (size_t)yb * n + x0, o);
                 va = na; vb = nb; vc = nc; vd = nd;
             }
@@ -476,7 +478,8 @@ B2R_DEV void sharpen_fix_f16_impl(const __half* __restrict__ pre, __half* __rest
     if (x0 >= n) return;
     const __half* plane = pre + (size_t)ch * dm.pre_plane;
     __half* oplane = out + (size_t)ch * dm.out_plane;
-    const __half2 up2 = __float2half2_rn(dm.up2), neg_s = __float2half2_rn(-dm.sharpen);
+    const __half2 up2 = __float2half2_rn(dm.up2);
+    const CasK ks = {dm.cas_a, dm.cas_b};
     const bool plane_end = (b >= dm.up_h);
     auto taps = [&](int y, CasRowH<NP>& t) {
         const __half* p = plane + (size_t)y * n + x0;
@@ -494,11 +497,11 @@ B2R_DEV void sharpen_fix_f16_impl(const __half* __restrict__ pre, __half* __rest
     taps(b - 2, ta);
     taps(b - 1, tb);
     taps(b, tc);
-    cas_row_f16<NP>(ta, tb, tc, neg_s, o);
+    cas_row_f16<NP>(ta, tb, tc, ks, o);
     store8(b - 1, o);
     if (!plane_end) {
         taps(b + 1, td);
-        cas_row_f16<NP>(tb, tc, td, neg_s, o);
+        cas_row_f16<NP>(tb, tc, td, ks, o);
         store8(b, o);
     }
     if (x0 + NP == n) {                // pixel (n-1, b-2)
@@ -509,7 +512,7 @@ B2R_DEV void sharpen_fix_f16_impl(const __half* __restrict__ pre, __half* __rest
         tm.b[0] = ta.b[3]; tm.link(__high2half(ta.b[2]), __high2half(ta.a[4]));
         tdn.b[0] = tb.b[3]; tdn.link(__high2half(tb.b[2]), __high2half(tb.a[4]));
         __half2 o1[1];
-        cas_row_f16<2>(tu, tm, tdn, neg_s, o1);
+        cas_row_f16<2>(tu, tm, tdn, ks, o1);
         oplane[(size_t)(b - 2) * n + n - 1] = __high2half(o1[0]);
     }
 }

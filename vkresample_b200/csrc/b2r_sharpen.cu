@@ -32,9 +32,11 @@ static cudaError_t launch_sharpen_fast(cudaStream_t s, const SharpenArgs& a) {
     static const int env_bx = env_or("B2R_SHARPEN_BX", 0);   // tuning aid (a multiple of 32)
     const int vecs = a.dm.up_w / np, bx = env_bx > 0 ? env_bx : cas_fast_block(vecs);
     dim3 block(bx), grid((vecs + bx - 1) / bx, (a.dm.up_h + ry - 1) / ry, 3);
-    if (a.precision == 2)
-        k_sharpen_fast_f16<8><<<grid, block, 0, s>>>((const __half*)a.pre, (__half*)a.out, a.dm, ry, reverse);
-    else if (np == 8)
+    if (a.precision == 2) {
+        static const int minb = env_or("B2R_SHARPEN_MINB", 3);   // 4: 64-register build, four resident CTAs (tuning aid)
+        if (minb == 4) k_sharpen_fast_f16<8, 4><<<grid, block, 0, s>>>((const __half*)a.pre, (__half*)a.out, a.dm, ry, reverse);
+        else k_sharpen_fast_f16<8><<<grid, block, 0, s>>>((const __half*)a.pre, (__half*)a.out, a.dm, ry, reverse);
+    } else if (np == 8)
         k_sharpen_fast_f32<2><<<grid, block, 0, s>>>((const float*)a.pre, (float*)a.out, a.dm, ry, reverse);
     else
         k_sharpen_fast_f32<1><<<grid, block, 0, s>>>((const float*)a.pre, (float*)a.out, a.dm, ry, reverse);
