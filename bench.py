@@ -403,7 +403,7 @@ def run_b200(args):
     # the SM issue rate is reported beside the byte roofline
     issue = None
     if dom == "c2r_sharpen" and args.config == "c2":
-        winst = 47.2e6
+        winst = 45.76e6
         t_issue = winst / (148 * 4 * 1.965e9)
         issue = {"warp_instructions_per_launch": winst, "issue_limit_us": round(t_issue * 1e6, 1),
                  "frac_of_issue_limit": round(t_issue / (pk[dom] * 1e-3), 3), "source": "ncu smsp__inst_executed.sum, profiles/r2_ncu_c2.md"}
