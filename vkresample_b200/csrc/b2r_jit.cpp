@@ -141,6 +141,23 @@ std::string cache_dir() {
     if (stat(d.c_str(), &st) != 0 || !S_ISDIR(st.st_mode) || st.st_uid != geteuid() || (st.st_mode & (S_IWGRP | S_IWOTH))) return "";
     return d;
 }
+// minimal structural check of a cubin image (ELF64, little endian): header present, section and program header
+// tables inside the image -- the driver walks them without knowing the buffer length
+bool cubin_is_sane_elf(const std::string& img) {
+    if (img.size() < 64 || memcmp(img.data(), "\x7f" "ELF", 4) != 0 || img[4] != 2 || img[5] != 1) return false;
+    auto rd = [&](size_t off, int bytes) { unsigned long long v = 0; memcpy(&v, img.data() + off, (size_t)bytes); return v; };
+    const unsigned long long phoff = rd(32, 8), shoff = rd(40, 8);
+    const unsigned long long phentsize = rd(54, 2), phnum = rd(56, 2), shentsize = rd(58, 2), shnum = rd(60, 2);
+    if (shoff > img.size() || shnum * shentsize > img.size() - shoff) return false;
+    if (phoff > img.size() || phnum * phentsize > img.size() - phoff) return false;
+    if (shentsize >= 64)
+        for (unsigned long long i = 0; i < shnum; ++i) {      // every section with file contents lies inside the image
+            const size_t sh = (size_t)(shoff + i * shentsize);
+            const unsigned long long type = rd(sh + 4, 4), off = rd(sh + 24, 8), size = rd(sh + 32, 8);
+            if (type != 8 /* SHT_NOBITS */ && (off > img.size() || size > img.size() - off)) return false;
+        }
+    return true;
+}
 // write `data` to `path` through a private temporary name; false (and nothing published) on any I/O error
 bool publish(const std::string& path, const std::string& data, const std::string& tag) {
     const std::string tmp = path + tag;
@@ -317,11 +334,22 @@ bool jit_build(const JitRequest& rq, JitModule** out_mod, RowImpl* r2c, ColImpl*
         if (attempt == 0 && !cdir.empty()) {
             cubin = slurp(cpath);
             if (!cubin.empty()) {
+                // cuModuleLoadData takes no length: a truncated file would make the driver read past the buffer.
+                // The .names file therefore starts with the size and checksum of the cubin it belongs to, and an
+                // image that does not match (or is not an ELF whose section table lies inside it) is never loaded.
                 std::istringstream nf(slurp(npath));
                 std::string line;
+                bool intact = false;
+                if (std::getline(nf, line)) {
+                    unsigned long long sz = 0, sum = 0;
+                    if (sscanf(line.c_str(), "#cubin %llu %llx", &sz, &sum) == 2)
+                        intact = sz == cubin.size() && sum == fnv(cubin) && cubin_is_sane_elf(cubin);
+                }
                 while (std::getline(nf, line)) if (!line.empty()) lowered.push_back(line);
-                if (lowered.size() != names.size()) { cubin.clear(); lowered.clear(); }
-                else from_cache = true;
+                if (!intact || lowered.size() != names.size()) {
+                    cubin.clear(); lowered.clear();
+                    remove(npath.c_str()); remove(cpath.c_str());
+                } else from_cache = true;
             }
         }
         if (cubin.empty()) {
@@ -358,7 +386,9 @@ bool jit_build(const JitRequest& rq, JitModule** out_mod, RowImpl* r2c, ColImpl*
             // names first, stream state checked, then rename; the .names file goes last and gates the cache hit
             if (!cdir.empty()) {
                 const std::string tag = "." + std::to_string((long long)getpid()) + "." + std::to_string((unsigned long long)(uintptr_t)&cubin);
-                std::string nm;
+                char head[64];
+                snprintf(head, sizeof head, "#cubin %llu %016llx\n", (unsigned long long)cubin.size(), (unsigned long long)fnv(cubin));
+                std::string nm = head;
                 for (const auto& l : lowered) nm += l + "\n";
                 if (publish(cpath, cubin, tag)) { if (!publish(npath, nm, tag)) remove(cpath.c_str()); }
             }
