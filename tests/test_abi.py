@@ -62,3 +62,29 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "import oracle" not in txt and "from oracle" not in txt and "oracle/" not in txt, f
+
+
+def test_cached_cubin_images_are_checked_before_loading(tmp_path):
+    """cuModuleLoadData takes no length, so a truncated file in the JIT cache must never reach it: the check the
+    cache applies (ELF64 header, section / program header tables and section contents inside the image) accepts a
+    real sm_100a cubin and rejects every truncation of it and garbage"""
+    import ctypes
+    import shutil
+    import subprocess
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        pytest.skip("no nvcc to make a cubin with")
+    src = tmp_path / "k.cu"
+    src.write_text("__global__ void k(float* p) { p[threadIdx.x] *= 2.f; }\n")
+    subprocess.run([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-cubin", "-o", str(tmp_path / "k.cubin"), str(src)],
+                   check=True, timeout=300)
+    img = (tmp_path / "k.cubin").read_bytes()
+    lib = vb.load_library()
+    ok = lib.b2r_debug_cubin_image_ok
+    ok.argtypes = [ctypes.c_char_p, ctypes.c_size_t]
+    ok.restype = ctypes.c_int
+    assert ok(img, len(img)) == 1
+    for n in (0, 1, 63, 64, 1000, len(img) // 2, len(img) - 1):
+        assert ok(img[:n], n) == 0, n
+    assert ok(b"x" * 5000, 5000) == 0
+    assert ok(b"\x7fELF" + b"\xff" * 4096, 4100) == 0

@@ -476,3 +476,10 @@ cudaError_t jit_launch_planar_to_u8(const JitModule* m, cudaStream_t s, const vo
 }
 
 }  // namespace b2r
+
+// Test hook (not part of include/b2resample.h): the structural check a cached cubin has to pass before it is
+// handed to the driver; tests/test_abi.py feeds it whole, truncated and garbage images.
+extern "C" int b2r_debug_cubin_image_ok(const void* image, size_t bytes) {
+    if (!image) return 0;
+    return b2r::cubin_is_sane_elf(std::string(static_cast<const char*>(image), bytes)) ? 1 : 0;
+}
